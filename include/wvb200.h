@@ -1,0 +1,244 @@
+/* wvb200.h -- C ABI of libwvb200.so, the B200-native (sm_100a) implementation of
+ * wayverb's two GPU hot loops:
+ *
+ *   wvb_wg_*  the rectilinear FDTD waveguide step
+ *             (replaces waveguide::run's device work,
+ *              reference src/waveguide/include/waveguide/waveguide.h:36-126 and the
+ *              condensed_waveguide kernel, src/waveguide/src/program.cpp:494-530)
+ *   wvb_rt_*  the stochastic ray-reflection loop
+ *             (replaces raytracer::run's device work,
+ *              reference src/raytracer/include/raytracer/raytracer.h:188-266 and the
+ *              reflections / stochastic kernels, src/raytracer/src/program.cpp:59-153,
+ *              src/raytracer/src/stochastic/program.cpp:58-152)
+ *
+ * The reference has no C ABI: its boundary is two C++14 function templates whose
+ * callback types leak OpenCL handles. The C++ shim in include/wayverb_b200/ keeps
+ * those templates' shape and sits on the functions declared here. Everything
+ * that crosses this boundary is a plain pointer, a size or one of the reference's
+ * own POD layouts (restated below with the file:line they mirror).
+ *
+ * Threading: one caller thread per handle (as threaded_engine.cpp:66 does);
+ * handles own their CUDA streams, device memory and (optionally) NCCL
+ * communicator. There is no CPU fallback: every entry point fails with
+ * WVB_ERR_NO_DEVICE / WVB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef WVB200_H
+#define WVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WVB_VERSION 100
+
+typedef enum {
+    WVB_OK = 0,
+    WVB_ERR_INVALID = 1,     /* bad argument / inconsistent mesh description   */
+    WVB_ERR_CUDA = 2,        /* a CUDA call failed; see wvb_last_error()        */
+    WVB_ERR_NO_DEVICE = 3,   /* no usable sm_100 GPU                            */
+    WVB_ERR_NCCL = 4,        /* NCCL missing or a call into it failed           */
+    WVB_ERR_UNSUPPORTED = 5, /* mesh too large for 32-bit node indices, ...     */
+    WVB_ERR_SIM = 6          /* the simulation raised error flags (see *_flags) */
+} wvb_status;
+
+/* ---- reference PODs (layouts are the drop-in contract) ------------------- */
+
+/* condensed_node, 8 B.  src/waveguide/include/waveguide/cl/structs.h:19-22 */
+typedef struct {
+    int32_t boundary_type;   /* bitmask below */
+    uint32_t boundary_index; /* index into boundary_index_array_N for N-d boundary nodes */
+} wvb_condensed_node;
+
+/* boundary_type bits.  src/waveguide/include/waveguide/cl/utils.h:11-21 */
+enum {
+    WVB_ID_NONE = 0,
+    WVB_ID_INSIDE = 1 << 0,
+    WVB_ID_NX = 1 << 1,
+    WVB_ID_PX = 1 << 2,
+    WVB_ID_NY = 1 << 3,
+    WVB_ID_PY = 1 << 4,
+    WVB_ID_NZ = 1 << 5,
+    WVB_ID_PZ = 1 << 6,
+    WVB_ID_REENTRANT = 1 << 7
+};
+
+/* error_code bits.  src/waveguide/include/waveguide/cl/structs.h:8-15 */
+enum {
+    WVB_FLAG_INF = 1 << 0,
+    WVB_FLAG_NAN = 1 << 1,
+    WVB_FLAG_OUTSIDE_RANGE = 1 << 2,
+    WVB_FLAG_OUTSIDE_MESH = 1 << 3,
+    WVB_FLAG_SUSPICIOUS_BOUNDARY = 1 << 4
+};
+
+/* coefficients_canonical (order 6), 112 B.
+ * src/waveguide/include/waveguide/cl/filter_structs.h:39-44,65-66 */
+typedef struct {
+    double b[7];
+    double a[7];
+} wvb_coefficients_canonical;
+
+/* boundary_data, 56 B.  src/waveguide/include/waveguide/cl/structs.h:38-41
+ * boundary_data_array_N is N of these back to back (:54-74). */
+typedef struct {
+    double filter_memory[6];
+    uint32_t coefficient_index;
+    uint32_t pad_;
+} wvb_boundary_data;
+
+/* ---- waveguide ------------------------------------------------------------ */
+
+typedef struct wvb_wg wvb_wg;
+
+/* kernel selection for the air-node stencil (wvb_wg_desc.flags, low byte) */
+enum {
+    WVB_WG_KERNEL_AUTO = 0,
+    WVB_WG_KERNEL_DIRECT = 1, /* register z-march, plain coalesced loads (bring-up / cross-check) */
+    WVB_WG_KERNEL_TMA = 2     /* TMA-staged shared-memory plane ring (the production kernel)       */
+};
+
+/* What waveguide::run receives through `mesh` (mesh.h:12-26, setup.h:27-85),
+ * restricted to the z-slab this handle owns. */
+typedef struct {
+    int32_t dim[3]; /* mesh_descriptor.dimensions (mesh_descriptor.h:14-20): x fastest */
+
+    /* slab owned by this handle: planes [z_begin, z_end) of the global mesh.
+     * A single-GPU run uses 0 and dim[2]. */
+    int32_t z_begin, z_end;
+
+    /* condensed nodes of planes [nodes_z0, nodes_z0 + nodes_nz) of the global
+     * mesh, x fastest; must cover [max(z_begin-1,0), min(z_end+1,dim[2])).
+     * Passing the whole mesh (nodes_z0 = 0, nodes_nz = dim[2]) is always fine. */
+    const wvb_condensed_node* nodes;
+    int32_t nodes_z0, nodes_nz;
+
+    /* one impedance filter per scene surface (vectors::get_coefficients()) */
+    const wvb_coefficients_canonical* coefficients;
+    uint32_t num_coefficients;
+
+    /* boundary_index_array_{1,2,3}: N coefficient indices per N-d boundary
+     * node, indexed by condensed_node.boundary_index - index_base[N-1]
+     * (index_base lets a slab pass only its own part of the arrays). */
+    const uint32_t* boundary_index[3];
+    uint64_t boundary_count[3];
+    uint32_t index_base[3];
+
+    int32_t device; /* CUDA ordinal */
+
+    /* multi-GPU: rank r owns a z-slab; ranks r-1 / r+1 own the adjacent slabs.
+     * nccl_unique_id = the 128 bytes of an ncclUniqueId shared by all ranks
+     * (NULL when nranks == 1). */
+    int32_t rank, nranks;
+    const void* nccl_unique_id;
+
+    uint32_t flags; /* WVB_WG_KERNEL_* | tuning bits; 0 = defaults */
+} wvb_wg_desc;
+
+/* Builds device state: two zeroed fp64 pressure arrays (waveguide.h:47-56),
+ * node classes, per-class boundary lists with zeroed filter memory and
+ * coefficient indices (setup.h:68-85). Copies everything it needs; the
+ * caller's arrays are not referenced after return and never modified. */
+wvb_status wvb_wg_create(const wvb_wg_desc* desc, wvb_wg** out);
+void wvb_wg_destroy(wvb_wg* wg);
+
+/* core::write_value / read_value on the `current` buffer (cl/common.h:42-57),
+ * `node` = global node index. Writes go to every local copy (owned plane or
+ * ghost plane) so all ranks may issue the same write. *owned (optional) tells
+ * whether this handle owns the node; a read of a node that is neither owned
+ * nor in a ghost plane returns 0.0 with *owned = 0. Both synchronise. */
+wvb_status wvb_wg_write_f64(wvb_wg* wg, uint64_t node, double value);
+wvb_status wvb_wg_read_f64(wvb_wg* wg, uint64_t node, double* value, int* owned);
+
+/* core::read_from_buffer on `current` (cl/common.h:35-40): the owned planes,
+ * dim[0]*dim[1]*(z_end-z_begin) values, x fastest. _f32 converts on the device
+ * (the GUI's pressure view, engine.cpp:160-168, is float). */
+wvb_status wvb_wg_read_field(wvb_wg* wg, double* out);
+wvb_status wvb_wg_read_field_f32(wvb_wg* wg, float* out);
+/* whole-field write to `current` (preprocessor::gaussian, gaussian.cpp:26-53) */
+wvb_status wvb_wg_write_field(wvb_wg* wg, const double* in);
+
+/* n iterations of { condensed_waveguide launch; swap } (waveguide.h:85-97,123)
+ * without callbacks. *error_flags (optional) receives the OR of the error_code
+ * bits raised; returns WVB_ERR_SIM when non-zero. Synchronises at the end. */
+wvb_status wvb_wg_step(wvb_wg* wg, uint32_t n_steps, int32_t* error_flags);
+
+/* The two halves of one iteration, for callers that run their own callbacks
+ * between them exactly like waveguide.h:80-124 does:
+ *   wvb_wg_launch  reset flag (:82), launch the kernel (:85-97) [+ ghost-plane
+ *                  exchange], read the flag back (:100); `current` still holds
+ *                  p(n) afterwards, `previous` holds p(n+1)
+ *   wvb_wg_swap    std::swap(previous, current) (:123)
+ * wvb_wg_step(n) == n x { launch; swap }. */
+wvb_status wvb_wg_launch(wvb_wg* wg, int32_t* error_flags);
+wvb_status wvb_wg_swap(wvb_wg* wg);
+
+/* The whole run loop (waveguide.h:80-124) for the stock processors, with the
+ * source and receivers executed on the device:
+ *   pre  = preprocessor::hard_source (soft = 0) or soft_source (soft = 1) at
+ *          source_node fed signal[0..n_steps)           (hard_source.h:17-23)
+ *   post = postprocessor::node at each receiver_nodes[r] (node.cpp:14-18):
+ *          out[step * n_receivers + r] = current[receiver] *before* the swap,
+ *          i.e. p(step) including the injected sample.
+ * Receivers a rank does not own are written as 0 (sum over ranks = full trace).
+ * *steps_done = n_steps unless an error flag stopped the run (checked every
+ * `check_interval` steps; 0 = only at the end). */
+typedef struct {
+    uint64_t source_node;
+    const double* signal;
+    uint32_t n_steps;
+    int32_t soft;
+    const uint64_t* receiver_nodes;
+    uint32_t n_receivers;
+    double* out;
+    uint32_t check_interval;
+} wvb_wg_run_params;
+wvb_status wvb_wg_run(wvb_wg* wg, const wvb_wg_run_params* p, uint32_t* steps_done,
+                      int32_t* error_flags);
+
+/* boundary_data_array_N readback in the reference layout (N records of 56 B
+ * per node, nodes in boundary_index order of this slab). count = nodes. */
+wvb_status wvb_wg_boundary_count(wvb_wg* wg, int n_dims, uint64_t* count);
+wvb_status wvb_wg_read_boundary_data(wvb_wg* wg, int n_dims, wvb_boundary_data* out);
+
+/* Device-side timing of n_steps plain steps (CUDA events on the handle's own
+ * stream, which is where the kernels are launched). Used by bench.py. */
+wvb_status wvb_wg_time_steps(wvb_wg* wg, uint32_t n_steps, float* milliseconds,
+                             int32_t* error_flags);
+
+/* introspection for bench / tests */
+typedef struct {
+    uint64_t local_nodes;       /* owned nodes                                  */
+    uint64_t air_nodes;         /* inside + reentrant                           */
+    uint64_t boundary_nodes[3]; /* 1-d, 2-d, 3-d                                */
+    uint64_t device_bytes;      /* device memory held by the handle             */
+    uint64_t kernel_launches;   /* launches of our kernels since create         */
+    int32_t kernel_variant;     /* WVB_WG_KERNEL_* actually in use              */
+    int32_t tile[3];            /* x, y tile and z chunk of the stencil kernel  */
+    int32_t sm_count;
+    int32_t pad_;
+} wvb_wg_info;
+wvb_status wvb_wg_get_info(wvb_wg* wg, wvb_wg_info* info);
+
+/* Synthetic cuboid room (BASELINE configs 2-4): writes the condensed nodes of
+ * planes [z0, z0+nz) of a dim[0] x dim[1] x dim[2] mesh whose outermost layer
+ * is id_none, next layer the boundary shell (faces 1-d, edges 2-d, corners
+ * 3-d; bit = side of the inner node) and the rest id_inside, numbered like
+ * boundary_coefficient_finder.cpp:12-19,129 (running count per class in node
+ * order over the WHOLE mesh). counts[3] (optional) = global class counts.
+ * Host-only helper; what compute_mesh (mesh.cpp:53-141) yields for a box. */
+wvb_status wvb_mesh_cuboid(const int32_t dim[3], int32_t z0, int32_t nz,
+                           wvb_condensed_node* nodes_out, uint64_t counts[3]);
+
+/* ---- misc ------------------------------------------------------------------ */
+int wvb_version(void);
+int wvb_device_count(void);
+/* text of the last failure on the calling thread ("" if none) */
+const char* wvb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WVB200_H */

@@ -1,0 +1,125 @@
+"""ctypes binding of libwvb200.so (the C ABI declared in include/wvb200.h).
+
+There is deliberately no fallback of any kind: if the shared library is missing
+or cannot be loaded the import of the product path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwvb200.so")
+
+# numpy views of the reference PODs (see include/wvb200.h for file:line)
+NODE_DT = np.dtype([("boundary_type", "<i4"), ("boundary_index", "<u4")])
+COEFF_DT = np.dtype([("b", "<f8", (7,)), ("a", "<f8", (7,))])
+BDATA_DT = np.dtype([("filter_memory", "<f8", (6,)), ("coefficient_index", "<u4"), ("pad", "<u4")])
+
+WVB_OK, WVB_ERR_INVALID, WVB_ERR_CUDA, WVB_ERR_NO_DEVICE, WVB_ERR_NCCL, WVB_ERR_UNSUPPORTED, WVB_ERR_SIM = range(7)
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+
+
+class WgDesc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32 * 3),
+        ("z_begin", C.c_int32), ("z_end", C.c_int32),
+        ("nodes", C.c_void_p),
+        ("nodes_z0", C.c_int32), ("nodes_nz", C.c_int32),
+        ("coefficients", C.c_void_p),
+        ("num_coefficients", C.c_uint32),
+        ("boundary_index", C.c_void_p * 3),
+        ("boundary_count", C.c_uint64 * 3),
+        ("index_base", C.c_uint32 * 3),
+        ("device", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("nccl_unique_id", C.c_void_p),
+        ("flags", C.c_uint32),
+    ]
+
+
+class WgRunParams(C.Structure):
+    _fields_ = [
+        ("source_node", C.c_uint64),
+        ("signal", C.c_void_p),
+        ("n_steps", C.c_uint32),
+        ("soft", C.c_int32),
+        ("receiver_nodes", C.c_void_p),
+        ("n_receivers", C.c_uint32),
+        ("out", C.c_void_p),
+        ("check_interval", C.c_uint32),
+    ]
+
+
+class WgInfo(C.Structure):
+    _fields_ = [
+        ("local_nodes", C.c_uint64), ("air_nodes", C.c_uint64),
+        ("boundary_nodes", C.c_uint64 * 3),
+        ("device_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("kernel_variant", C.c_int32), ("tile", C.c_int32 * 3),
+        ("sm_count", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+# every symbol include/wvb200.h declares (tests check the .so exports them all)
+WG_SYMBOLS = [
+    "wvb_wg_create", "wvb_wg_destroy", "wvb_wg_write_f64", "wvb_wg_read_f64", "wvb_wg_read_field",
+    "wvb_wg_read_field_f32", "wvb_wg_write_field", "wvb_wg_step", "wvb_wg_launch", "wvb_wg_swap",
+    "wvb_wg_run",
+    "wvb_wg_boundary_count", "wvb_wg_read_boundary_data", "wvb_wg_time_steps", "wvb_wg_get_info",
+    "wvb_mesh_cuboid", "wvb_version", "wvb_device_count", "wvb_last_error",
+]
+
+_lib = None
+
+
+class WvbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("wvb status %d: %s" % (status, message))
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build it with `python -m wayverb_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    L.wvb_version.restype = C.c_int
+    L.wvb_device_count.restype = C.c_int
+    L.wvb_last_error.restype = C.c_char_p
+    L.wvb_wg_create.argtypes = [C.POINTER(WgDesc), C.POINTER(vp)]
+    L.wvb_wg_destroy.argtypes = [vp]
+    L.wvb_wg_destroy.restype = None
+    L.wvb_wg_write_f64.argtypes = [vp, u64, C.c_double]
+    L.wvb_wg_read_f64.argtypes = [vp, u64, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.wvb_wg_read_field.argtypes = [vp, vp]
+    L.wvb_wg_read_field_f32.argtypes = [vp, vp]
+    L.wvb_wg_write_field.argtypes = [vp, vp]
+    L.wvb_wg_step.argtypes = [vp, u32, C.POINTER(i32)]
+    L.wvb_wg_launch.argtypes = [vp, C.POINTER(i32)]
+    L.wvb_wg_swap.argtypes = [vp]
+    L.wvb_wg_run.argtypes = [vp, C.POINTER(WgRunParams), C.POINTER(u32), C.POINTER(i32)]
+    L.wvb_wg_boundary_count.argtypes = [vp, C.c_int, C.POINTER(u64)]
+    L.wvb_wg_read_boundary_data.argtypes = [vp, C.c_int, vp]
+    L.wvb_wg_time_steps.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.wvb_wg_get_info.argtypes = [vp, C.POINTER(WgInfo)]
+    L.wvb_mesh_cuboid.argtypes = [C.POINTER(i32 * 3), i32, i32, vp, C.POINTER(u64 * 3)]
+    _lib = L
+    return L
+
+
+def check(status, allow_sim=False):
+    if status == WVB_OK or (allow_sim and status == WVB_ERR_SIM):
+        return status
+    raise WvbError(status, lib().wvb_last_error().decode())
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

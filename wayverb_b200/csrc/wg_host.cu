@@ -1,0 +1,897 @@
+// wg_host.cu -- host side of the waveguide path behind the C ABI (include/wvb200.h).
+//
+// Restates, B200-first, what waveguide::run does around its kernel launch
+// (reference src/waveguide/include/waveguide/waveguide.h:36-126):
+//   :47-56   two zeroed pressure buffers          -> P[0], P[1] (fp64, padded, ghost planes)
+//   :58-71   nodes / coefficients / boundary data -> class bytes + per-class boundary lists
+//   :80-124  per-step loop                        -> enqueue_step() (+ device-side source /
+//                                                    receivers in wvb_wg_run)
+// and adds what the reference does not have: z-slab ownership with one
+// ghost-plane exchange per step (NCCL send/recv between z-neighbours).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "nccl_dyn.h"
+#include "wg_kernels.cuh"
+
+namespace wvb {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+namespace {
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+                    cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (encode_tiled_fn) nullptr;
+        }
+        return reinterpret_cast<encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+struct blist_host {
+    std::vector<uint32_t> off, meta, ci, bidx;
+};
+
+}  // namespace
+}  // namespace wvb
+
+using namespace wvb;
+
+struct wvb_wg {
+    int dev = 0;
+    int dim[3] = {0, 0, 0};
+    int z_begin = 0, z_end = 0;
+    int rank = 0, nranks = 1;
+    WgGeom g{};
+    dev_buf<double> P[2];
+    int cur = 0;  // P[cur] is `current`, P[cur ^ 1] is `previous`
+    dev_buf<uint8_t> code;
+    struct list_t {
+        uint32_t n = 0;
+        dev_buf<uint32_t> off, meta, ci;
+        dev_buf<double> mem;
+        std::vector<uint32_t> bidx;
+    } bl[3];
+    dev_buf<wvb_coefficients_canonical> coeffs;
+    dev_buf<int> flag;
+    dev_buf<int> flag5;
+    int* h_flag = nullptr;  // pinned, 8 ints
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    CUtensorMap map[2];
+    int variant = WVB_WG_KERNEL_DIRECT;
+    int ty = 8, nstage = 5, zchunks = 1;
+    int sm_count = 0;
+    nccl::comm_t comm = nullptr;
+    size_t device_bytes = 0;
+    uint64_t launches = 0;
+    uint64_t air_nodes = 0;
+    double courant = 0, courant_sq = 0;
+
+    ~wvb_wg() {
+        cudaSetDevice(dev);
+        if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+        if (h_flag) cudaFreeHost(h_flag);
+    }
+};
+
+namespace {
+
+// ---- static analysis of one boundary node -----------------------------------
+// Everything boundary_N learns from nodes[] / dimensions is fixed at setup:
+// inner ports (program.cpp:18-87), which ports leave the mesh
+// (get_inner_pressure :243-247, get_summed_surrounding :198-201) and whether a
+// surrounding node is not itself a boundary (:202-205).
+struct node_view {
+    const wvb_condensed_node* nodes;  // plane nodes_z0 first
+    int nodes_z0, nodes_nz;
+    int dx, dy, dz;
+    int32_t type_at(int x, int y, int z) const {
+        return nodes[((size_t)(z - nodes_z0) * dy + y) * dx + x].boundary_type;
+    }
+};
+
+inline void legal_dirs(int32_t bt, int n_expected, int out[3]) {
+    out[0] = out[1] = out[2] = 6;
+    if (bt & ~(WVB_ID_NX | WVB_ID_PX | WVB_ID_NY | WVB_ID_PY | WVB_ID_NZ | WVB_ID_PZ)) return;
+    int found[3], n = 0;
+    for (int axis = 0; axis < 3; ++axis) {
+        const bool hn = bt & (WVB_ID_NX << (2 * axis));
+        const bool hp = bt & (WVB_ID_PX << (2 * axis));
+        if (hn && hp) return;
+        if (hn) found[n++] = 2 * axis;
+        else if (hp) found[n++] = 2 * axis + 1;
+    }
+    if (n != n_expected) return;
+    for (int i = 0; i < n; ++i) out[i] = found[i];
+}
+
+inline uint32_t analyse_boundary_node(const node_view& v, int x, int y, int z, int32_t bt, int N) {
+    int port[3];
+    legal_dirs(bt, N, port);
+    uint32_t meta = 0;
+    for (int i = 0; i < 3; ++i) meta |= uint32_t(i < N ? port[i] : 6) << (3 * i);
+    static const int dxs[6] = {-1, 1, 0, 0, 0, 0}, dys[6] = {0, 0, -1, 1, 0, 0},
+                     dzs[6] = {0, 0, 0, 0, -1, 1};
+    uint32_t inmesh = 0;
+    for (int p = 0; p < 6; ++p) {
+        const int nx = x + dxs[p], ny = y + dys[p], nz = z + dzs[p];
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < v.dx && ny < v.dy && nz < v.dz) inmesh |= 1u << p;
+    }
+    meta |= inmesh << META_PORTMASK_SHIFT;
+    for (int i = 0; i < N; ++i) {
+        if (port[i] < 6 && !((inmesh >> port[i]) & 1u)) meta |= META_ERR_OUTSIDE;
+    }
+    if (N < 3) {
+        int sp[4], ns;
+        if (N == 1) {
+            ns = 4;
+            const int ax = port[0] >> 1;
+            if (ax == 0) { sp[0] = 2; sp[1] = 3; sp[2] = 4; sp[3] = 5; }
+            else if (ax == 1) { sp[0] = 0; sp[1] = 1; sp[2] = 4; sp[3] = 5; }
+            else if (ax == 2) { sp[0] = 0; sp[1] = 1; sp[2] = 2; sp[3] = 3; }
+            else { sp[0] = sp[1] = sp[2] = sp[3] = 6; }
+        } else {
+            ns = 2;
+            const bool hx = (port[0] >> 1) == 0 || (port[1] >> 1) == 0;
+            const bool hy = (port[0] >> 1) == 1 || (port[1] >> 1) == 1;
+            if (hx) {
+                if (hy) { sp[0] = 4; sp[1] = 5; }
+                else { sp[0] = 2; sp[1] = 3; }
+            } else { sp[0] = 0; sp[1] = 1; }
+        }
+        for (int i = 0; i < ns; ++i) {
+            if (sp[i] >= 6) continue;  // "-1": the node itself, a boundary node, in the mesh
+            if (!((inmesh >> sp[i]) & 1u)) {
+                meta |= META_ERR_OUTSIDE | META_SURROUND_ZERO;
+                break;
+            }
+            const int32_t t = v.type_at(x + dxs[sp[i]], y + dys[sp[i]], z + dzs[sp[i]]);
+            if (t == WVB_ID_NONE || t == WVB_ID_INSIDE) meta |= META_ERR_SUSPICIOUS;
+        }
+    }
+    return meta;
+}
+
+inline int node_class(int32_t bt, int* ndims) {
+    const int pc = __builtin_popcount((uint32_t)bt);
+    *ndims = 0;
+    if (pc == 1 && ((bt & WVB_ID_INSIDE) || (bt & WVB_ID_REENTRANT))) return CLS_AIR;
+    if (pc >= 1 && pc <= 3) {
+        *ndims = pc;
+        return CLS_BOUNDARY;
+    }
+    return CLS_NONE;
+}
+
+// ---- launch configuration ------------------------------------------------------
+template <class Cfg>
+void set_tma_attr() {
+    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
+}
+template <class Cfg>
+int tma_occupancy() {
+    int nb = 0;
+    WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg>, Cfg::THREADS,
+                                                           Cfg::SMEM_BYTES));
+    return nb;
+}
+
+int pick_zchunks(long long tiles, int nzl, int slots, int min_len) {
+    if (tiles >= 4LL * slots) return 1;
+    int best = 1;
+    double best_score = -1;
+    const int max_zc = std::max(1, nzl / min_len);
+    for (int zc = 1; zc <= max_zc; ++zc) {
+        const double waves = double(tiles) * zc / slots;
+        const double eff = waves / std::ceil(waves);
+        const double halo = 1.0 - 1.0 / (double(nzl) / zc + 2.0);  // 2 extra planes per chunk, ~half missed
+        const double score = eff * halo;
+        if (score > best_score + 1e-9) {
+            best_score = score;
+            best = zc;
+        }
+    }
+    return best;
+}
+
+void make_tensor_map(wvb_wg* w, int which, int ty) {
+    encode_tiled_fn enc = get_encode_tiled();
+    WVB_REQUIRE(enc != nullptr, WVB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    const WgGeom& g = w->g;
+    cuuint64_t gdim[3] = {(cuuint64_t)g.dx, (cuuint64_t)g.dy, (cuuint64_t)(g.nzl + 2)};
+    cuuint64_t gstr[2] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.plane * 8};
+    cuuint32_t box[3] = {132, (cuuint32_t)(ty + 2), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&w->map[which], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, w->P[which].p, gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WVB_REQUIRE(r == CUDA_SUCCESS, WVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+}
+
+template <class Cfg>
+void launch_tma(wvb_wg* w, const double* cur, double* prev) {
+    const WgGeom& g = w->g;
+    dim3 grid((g.dx + Cfg::TX - 1) / Cfg::TX, (g.dy + Cfg::TY - 1) / Cfg::TY, w->zchunks);
+    wg_air_tma<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
+            w->map[w->cur], cur, prev, w->code.p, g, w->zchunks, w->flag.p);
+}
+
+void launch_air(wvb_wg* w, const double* cur, double* prev) {
+    const WgGeom& g = w->g;
+    if (w->variant == WVB_WG_KERNEL_TMA) {
+        if (w->ty == 16) {
+            if (w->nstage == 4) launch_tma<TmaCfg<16, 4>>(w, cur, prev);
+            else launch_tma<TmaCfg<16, 5>>(w, cur, prev);
+        } else {
+            if (w->nstage == 4) launch_tma<TmaCfg<8, 4>>(w, cur, prev);
+            else if (w->nstage == 6) launch_tma<TmaCfg<8, 6>>(w, cur, prev);
+            else launch_tma<TmaCfg<8, 5>>(w, cur, prev);
+        }
+    } else {
+        constexpr int BX = 32, BY = 8;
+        const int zchunk = (g.nzl + w->zchunks - 1) / w->zchunks;
+        dim3 grid(((g.dx + 1) / 2 + BX - 1) / BX, (g.dy + BY - 1) / BY, (g.nzl + zchunk - 1) / zchunk);
+        wg_air_direct<BX, BY><<<grid, dim3(BX, BY), 0, w->stream>>>(cur, prev, w->code.p, g, zchunk,
+                                                                     w->flag.p);
+    }
+    w->launches++;
+}
+
+template <int N>
+void launch_boundary(wvb_wg* w, const double* cur, double* prev) {
+    auto& l = w->bl[N - 1];
+    if (!l.n) return;
+    BList L{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
+    wg_boundary<N><<<(l.n + 127) / 128, 128, 0, w->stream>>>(cur, prev, L, w->coeffs.p, w->g,
+                                                              w->courant, w->courant_sq, w->flag.p);
+    w->launches++;
+}
+
+void nccl_check(int r, const char* what) {
+    if (r != nccl::success) {
+        set_last_error("%s failed: %s", what, nccl::get().GetErrorString(r));
+        throw status_error{WVB_ERR_NCCL};
+    }
+}
+
+// one ghost-plane exchange of array `a` (both faces) with the z-neighbours
+void exchange_ghosts(wvb_wg* w, double* a) {
+    if (w->nranks <= 1) return;
+    auto& n = nccl::get();
+    const size_t cnt = (size_t)w->g.plane;
+    nccl_check(n.GroupStart(), "ncclGroupStart");
+    if (w->rank > 0) {
+        nccl_check(n.Send(a + cnt, cnt, nccl::t_float64, w->rank - 1, w->comm, w->stream), "ncclSend");
+        nccl_check(n.Recv(a, cnt, nccl::t_float64, w->rank - 1, w->comm, w->stream), "ncclRecv");
+    }
+    if (w->rank < w->nranks - 1) {
+        nccl_check(n.Send(a + cnt * w->g.nzl, cnt, nccl::t_float64, w->rank + 1, w->comm, w->stream),
+                   "ncclSend");
+        nccl_check(n.Recv(a + cnt * (w->g.nzl + 1), cnt, nccl::t_float64, w->rank + 1, w->comm,
+                          w->stream),
+                   "ncclRecv");
+    }
+    nccl_check(n.GroupEnd(), "ncclGroupEnd");
+}
+
+// condensed_waveguide launch (waveguide.h:85-97), enqueue only: afterwards
+// `previous` holds p(n+1) and its ghost planes are up to date
+void enqueue_launch(wvb_wg* w) {
+    const double* cur = w->P[w->cur].p;
+    double* prev = w->P[w->cur ^ 1].p;
+    launch_air(w, cur, prev);
+    launch_boundary<1>(w, cur, prev);
+    launch_boundary<2>(w, cur, prev);
+    launch_boundary<3>(w, cur, prev);
+    exchange_ghosts(w, prev);
+}
+// launch + swap (waveguide.h:123)
+void enqueue_step(wvb_wg* w) {
+    enqueue_launch(w);
+    w->cur ^= 1;
+}
+
+// flag readback (waveguide.h:100), OR-reduced over ranks
+int fetch_flags(wvb_wg* w) {
+    if (w->nranks > 1) {
+        flag_expand<<<1, 32, 0, w->stream>>>(w->flag.p, w->flag5.p);
+        nccl_check(nccl::get().AllReduce(w->flag5.p, w->flag5.p, 5, nccl::t_int32, nccl::op_max,
+                                         w->comm, w->stream),
+                   "ncclAllReduce");
+        WVB_CUDA(cudaMemcpyAsync(w->h_flag, w->flag5.p, 5 * sizeof(int), cudaMemcpyDeviceToHost,
+                                 w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+        int f = 0;
+        for (int i = 0; i < 5; ++i) f |= (w->h_flag[i] ? 1 : 0) << i;
+        return f;
+    }
+    WVB_CUDA(cudaMemcpyAsync(w->h_flag, w->flag.p, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    WVB_CUDA(cudaStreamSynchronize(w->stream));
+    return w->h_flag[0];
+}
+
+// local element offset of a global node, or -1 when this handle holds no copy
+long long local_offset(const wvb_wg* w, uint64_t node, int* owned) {
+    const uint64_t dx = w->dim[0], dy = w->dim[1];
+    const int x = int(node % dx);
+    const uint64_t r = node / dx;
+    const int y = int(r % dy);
+    const long long z = (long long)(r / dy);
+    if (owned) *owned = 0;
+    if (z >= w->dim[2]) return -1;
+    const long long lz = z - w->z_begin + 1;
+    if (lz < 0 || lz > w->g.nzl + 1) return -1;
+    if (owned) *owned = (lz >= 1 && lz <= w->g.nzl);
+    return (lz * w->g.dy + y) * w->g.px + x;
+}
+
+void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
+    WVB_REQUIRE(d != nullptr, WVB_ERR_INVALID, "null descriptor");
+    const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
+    WVB_REQUIRE(dx > 0 && dy > 0 && dz > 0, WVB_ERR_INVALID, "bad dimensions %d %d %d", dx, dy, dz);
+    WVB_REQUIRE((uint64_t)dx * dy * dz < 0xffffffffull, WVB_ERR_UNSUPPORTED,
+                "mesh exceeds 32-bit node indices (cl/utils.cpp:38)");
+    WVB_REQUIRE(0 <= d->z_begin && d->z_begin < d->z_end && d->z_end <= dz, WVB_ERR_INVALID,
+                "bad slab [%d,%d) of %d", d->z_begin, d->z_end, dz);
+    WVB_REQUIRE(d->nodes != nullptr && d->coefficients != nullptr && d->num_coefficients > 0,
+                WVB_ERR_INVALID, "nodes / coefficients missing");
+    const int need_lo = std::max(d->z_begin - 1, 0), need_hi = std::min(d->z_end + 1, dz);
+    WVB_REQUIRE(d->nodes_z0 <= need_lo && d->nodes_z0 + d->nodes_nz >= need_hi, WVB_ERR_INVALID,
+                "nodes cover planes [%d,%d) but [%d,%d) are needed", d->nodes_z0,
+                d->nodes_z0 + d->nodes_nz, need_lo, need_hi);
+    WVB_REQUIRE(d->nranks >= 1 && d->rank >= 0 && d->rank < d->nranks, WVB_ERR_INVALID, "bad rank");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device visible (this library has no CPU fallback)");
+        throw status_error{WVB_ERR_NO_DEVICE};
+    }
+    WVB_REQUIRE(d->device >= 0 && d->device < ndev, WVB_ERR_NO_DEVICE, "device %d of %d", d->device,
+                ndev);
+    cudaDeviceProp prop;
+    WVB_CUDA(cudaGetDeviceProperties(&prop, d->device));
+    WVB_REQUIRE(prop.major == 10, WVB_ERR_NO_DEVICE,
+                "device %d is sm_%d%d; this build carries sm_100a code only", d->device, prop.major,
+                prop.minor);
+    WVB_CUDA(cudaSetDevice(d->device));
+
+    w->dev = d->device;
+    w->dim[0] = dx; w->dim[1] = dy; w->dim[2] = dz;
+    w->z_begin = d->z_begin; w->z_end = d->z_end;
+    w->rank = d->rank; w->nranks = d->nranks;
+    w->sm_count = prop.multiProcessorCount;
+    w->courant = 1.0 / std::sqrt(3.0);  // program.cpp:12, in the pressure type
+    w->courant_sq = 1.0 / 3.0;          // program.cpp:13
+
+    WgGeom& g = w->g;
+    g.dx = dx; g.dy = dy; g.nzl = d->z_end - d->z_begin;
+    g.px = (dx + 1) & ~1;
+    g.pc = (dx + 15) & ~15;
+    g.plane = (long long)g.px * dy;
+    g.cplane = (long long)g.pc * dy;
+    const long long total = g.plane * (g.nzl + 2);
+    WVB_REQUIRE(total < 0xffffffffll, WVB_ERR_UNSUPPORTED, "slab too large for 32-bit offsets");
+
+    // ---- digest the nodes: class bytes + boundary lists (node order) ----------
+    const node_view nv{d->nodes, d->nodes_z0, d->nodes_nz, dx, dy, dz};
+    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), CLS_NONE);
+    std::vector<std::array<uint32_t, 3>> plane_counts(g.nzl);
+    std::vector<uint64_t> plane_air(g.nzl, 0);
+    parallel_for(g.nzl, [&](int64_t lp) {
+        const int z = d->z_begin + (int)lp;
+        std::array<uint32_t, 3> c{0, 0, 0};
+        uint64_t air = 0;
+        uint8_t* crow = code.data() + (size_t)(lp + 1) * g.cplane;
+        for (int y = 0; y < dy; ++y) {
+            for (int x = 0; x < dx; ++x) {
+                int nd;
+                const int cls = node_class(nv.type_at(x, y, z), &nd);
+                crow[(size_t)y * g.pc + x] = (uint8_t)cls;
+                if (cls == CLS_BOUNDARY) c[nd - 1]++;
+                if (cls == CLS_AIR) air++;
+            }
+        }
+        plane_counts[lp] = c;
+        plane_air[lp] = air;
+    });
+    std::vector<std::array<uint32_t, 3>> plane_start(g.nzl);
+    uint32_t tot[3] = {0, 0, 0};
+    for (int lp = 0; lp < g.nzl; ++lp) {
+        for (int k = 0; k < 3; ++k) {
+            plane_start[lp][k] = tot[k];
+            tot[k] += plane_counts[lp][k];
+        }
+        w->air_nodes += plane_air[lp];
+    }
+    blist_host hl[3];
+    for (int k = 0; k < 3; ++k) {
+        hl[k].off.resize(tot[k]);
+        hl[k].meta.resize(tot[k]);
+        hl[k].bidx.resize(tot[k]);
+        hl[k].ci.resize((size_t)tot[k] * (k + 1));
+    }
+    std::vector<int> bad_plane(g.nzl, 0);
+    parallel_for(g.nzl, [&](int64_t lp) {
+        const int z = d->z_begin + (int)lp;
+        uint32_t pos[3] = {plane_start[lp][0], plane_start[lp][1], plane_start[lp][2]};
+        for (int y = 0; y < dy; ++y) {
+            for (int x = 0; x < dx; ++x) {
+                const wvb_condensed_node nd =
+                        d->nodes[((size_t)(z - d->nodes_z0) * dy + y) * dx + x];
+                int N;
+                if (node_class(nd.boundary_type, &N) != CLS_BOUNDARY) continue;
+                const int k = N - 1;
+                const uint32_t t = pos[k]++;
+                hl[k].off[t] = (uint32_t)(((long long)(lp + 1) * dy + y) * g.px + x);
+                hl[k].meta[t] = analyse_boundary_node(nv, x, y, z, nd.boundary_type, N);
+                hl[k].bidx[t] = nd.boundary_index;
+                const uint64_t rel = (uint64_t)nd.boundary_index - d->index_base[k];
+                if (nd.boundary_index < d->index_base[k] || rel >= d->boundary_count[k] ||
+                    d->boundary_index[k] == nullptr) {
+                    bad_plane[lp] = 1;
+                    continue;
+                }
+                for (int i = 0; i < N; ++i) {
+                    const uint32_t c = d->boundary_index[k][rel * N + i];
+                    if (c >= d->num_coefficients) bad_plane[lp] = 2;
+                    hl[k].ci[(size_t)i * tot[k] + t] = c;
+                }
+            }
+        }
+    });
+    for (int lp = 0; lp < g.nzl; ++lp) {
+        WVB_REQUIRE(bad_plane[lp] != 1, WVB_ERR_INVALID,
+                    "a boundary node's boundary_index is outside boundary_index_array (plane %d)",
+                    d->z_begin + lp);
+        WVB_REQUIRE(bad_plane[lp] != 2, WVB_ERR_INVALID,
+                    "a coefficient index exceeds num_coefficients (plane %d)", d->z_begin + lp);
+    }
+
+    // ---- device state ------------------------------------------------------------
+    WVB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    WVB_CUDA(cudaEventCreate(&w->ev0));
+    WVB_CUDA(cudaEventCreate(&w->ev1));
+    WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
+    w->P[0].alloc((size_t)total, true, &w->device_bytes);
+    w->P[1].alloc((size_t)total, true, &w->device_bytes);
+    w->code.upload(code.data(), code.size(), &w->device_bytes);
+    w->coeffs.upload(d->coefficients, d->num_coefficients, &w->device_bytes);
+    w->flag.alloc(1, true, &w->device_bytes);
+    w->flag5.alloc(8, true, &w->device_bytes);
+    for (int k = 0; k < 3; ++k) {
+        auto& l = w->bl[k];
+        l.n = tot[k];
+        l.off.upload(hl[k].off.data(), hl[k].off.size(), &w->device_bytes);
+        l.meta.upload(hl[k].meta.data(), hl[k].meta.size(), &w->device_bytes);
+        l.ci.upload(hl[k].ci.data(), hl[k].ci.size(), &w->device_bytes);
+        l.mem.alloc((size_t)tot[k] * (k + 1) * 6, true, &w->device_bytes);  // setup.h:68-76: zeroed
+        l.bidx = std::move(hl[k].bidx);
+    }
+
+    // ---- kernel variant + launch shape ----------------------------------------------
+    int want = d->flags & 0xff;
+    const char* ev = getenv("WVB_WG_KERNEL");
+    if (ev && !strcmp(ev, "direct")) want = WVB_WG_KERNEL_DIRECT;
+    if (ev && !strcmp(ev, "tma")) want = WVB_WG_KERNEL_TMA;
+    const bool tma_fits = dx >= 132 && dy >= 10;
+    if (want == WVB_WG_KERNEL_AUTO) want = tma_fits ? WVB_WG_KERNEL_TMA : WVB_WG_KERNEL_DIRECT;
+    w->variant = want;
+    w->ty = env_int("WVB_WG_TY", ((d->flags >> 8) & 0xff) ? ((d->flags >> 8) & 0xff) : 8);
+    w->nstage = env_int("WVB_WG_STAGES", 5);
+    if (w->ty != 16) w->ty = 8;
+    if (w->ty == 16 && w->nstage != 4) w->nstage = 5;
+    if (w->nstage != 4 && w->nstage != 6) w->nstage = 5;
+    int slots;
+    long long tiles;
+    if (w->variant == WVB_WG_KERNEL_TMA) {
+        set_tma_attr<TmaCfg<8, 4>>();
+        set_tma_attr<TmaCfg<8, 5>>();
+        set_tma_attr<TmaCfg<8, 6>>();
+        set_tma_attr<TmaCfg<16, 4>>();
+        set_tma_attr<TmaCfg<16, 5>>();
+        make_tensor_map(w, 0, w->ty);
+        make_tensor_map(w, 1, w->ty);
+        int occ;
+        if (w->ty == 16) occ = w->nstage == 4 ? tma_occupancy<TmaCfg<16, 4>>() : tma_occupancy<TmaCfg<16, 5>>();
+        else occ = w->nstage == 4 ? tma_occupancy<TmaCfg<8, 4>>()
+                 : w->nstage == 6 ? tma_occupancy<TmaCfg<8, 6>>() : tma_occupancy<TmaCfg<8, 5>>();
+        slots = std::max(1, occ) * w->sm_count;
+        tiles = (long long)((dx + 127) / 128) * ((dy + w->ty - 1) / w->ty);
+    } else {
+        slots = 8 * w->sm_count;
+        tiles = (long long)(((dx + 1) / 2 + 31) / 32) * ((dy + 7) / 8);
+    }
+    const int zc_req = env_int("WVB_WG_ZCHUNKS", (int)((d->flags >> 16) & 0xfff));
+    w->zchunks = zc_req > 0 ? std::min(zc_req, g.nzl) : pick_zchunks(tiles, g.nzl, slots, 12);
+
+    // ---- NCCL ---------------------------------------------------------------------------
+    if (w->nranks > 1) {
+        WVB_REQUIRE(d->nccl_unique_id != nullptr, WVB_ERR_INVALID, "nranks > 1 needs an ncclUniqueId");
+        WVB_REQUIRE(nccl::get().ok, WVB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+        nccl::unique_id id;
+        memcpy(&id, d->nccl_unique_id, sizeof id);
+        nccl_check(nccl::get().CommInitRank(&w->comm, w->nranks, id, w->rank), "ncclCommInitRank");
+    }
+    WVB_CUDA(cudaDeviceSynchronize());
+}
+
+template <class F>
+wvb_status guarded(F&& f) {
+    try {
+        f();
+        return WVB_OK;
+    } catch (const status_error& e) {
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return WVB_ERR_INVALID;
+    } catch (const std::exception& e) {
+        set_last_error("%s", e.what());
+        return WVB_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// =================================================================================
+// C ABI
+// =================================================================================
+extern "C" {
+
+int wvb_version(void) { return WVB_VERSION; }
+
+int wvb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* wvb_last_error(void) { return g_last_error.c_str(); }
+
+wvb_status wvb_wg_create(const wvb_wg_desc* desc, wvb_wg** out) {
+    if (!out) return WVB_ERR_INVALID;
+    *out = nullptr;
+    auto w = std::make_unique<wvb_wg>();
+    const wvb_status s = guarded([&] { create_impl(desc, w.get()); });
+    if (s == WVB_OK) *out = w.release();
+    return s;
+}
+
+void wvb_wg_destroy(wvb_wg* wg) { delete wg; }
+
+wvb_status wvb_wg_write_f64(wvb_wg* w, uint64_t node, double value) {
+    if (!w) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        const long long off = local_offset(w, node, nullptr);
+        if (off < 0) return;
+        WVB_CUDA(cudaMemcpyAsync(w->P[w->cur].p + off, &value, sizeof(double),
+                                 cudaMemcpyHostToDevice, w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+}
+
+wvb_status wvb_wg_read_f64(wvb_wg* w, uint64_t node, double* value, int* owned) {
+    if (!w || !value) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        int own = 0;
+        const long long off = local_offset(w, node, &own);
+        if (owned) *owned = own;
+        *value = 0.0;
+        if (off < 0) return;
+        WVB_CUDA(cudaMemcpyAsync(value, w->P[w->cur].p + off, sizeof(double), cudaMemcpyDeviceToHost,
+                                 w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+}
+
+wvb_status wvb_wg_read_field(wvb_wg* w, double* out) {
+    if (!w || !out) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        const WgGeom& g = w->g;
+        WVB_CUDA(cudaMemcpy2DAsync(out, (size_t)g.dx * 8, w->P[w->cur].p + g.plane, (size_t)g.px * 8,
+                                   (size_t)g.dx * 8, (size_t)g.dy * g.nzl, cudaMemcpyDeviceToHost,
+                                   w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+}
+
+wvb_status wvb_wg_read_field_f32(wvb_wg* w, float* out) {
+    if (!w || !out) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        const WgGeom& g = w->g;
+        const size_t n = (size_t)g.dx * g.dy * g.nzl;
+        dev_buf<float> tmp;
+        tmp.alloc(n, false);
+        wg_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>(w->P[w->cur].p, tmp.p, g);
+        w->launches++;
+        WVB_CUDA(cudaMemcpyAsync(out, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+}
+
+wvb_status wvb_wg_write_field(wvb_wg* w, const double* in) {
+    if (!w || !in) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        const WgGeom& g = w->g;
+        double* cur = w->P[w->cur].p;
+        WVB_CUDA(cudaMemcpy2DAsync(cur + g.plane, (size_t)g.px * 8, in, (size_t)g.dx * 8,
+                                   (size_t)g.dx * 8, (size_t)g.dy * g.nzl, cudaMemcpyHostToDevice,
+                                   w->stream));
+        exchange_ghosts(w, cur);
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+}
+
+wvb_status wvb_wg_step(wvb_wg* w, uint32_t n_steps, int32_t* error_flags) {
+    if (!w) return WVB_ERR_INVALID;
+    int flags = 0;
+    wvb_status s = guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));  // waveguide.h:82
+        for (uint32_t i = 0; i < n_steps; ++i) enqueue_step(w);
+        WVB_CUDA(cudaGetLastError());
+        flags = fetch_flags(w);
+    });
+    if (error_flags) *error_flags = flags;
+    if (s == WVB_OK && flags) {
+        set_last_error("simulation raised error flags 0x%x", flags);
+        s = WVB_ERR_SIM;
+    }
+    return s;
+}
+
+wvb_status wvb_wg_launch(wvb_wg* w, int32_t* error_flags) {
+    if (!w) return WVB_ERR_INVALID;
+    int flags = 0;
+    wvb_status s = guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
+        enqueue_launch(w);
+        WVB_CUDA(cudaGetLastError());
+        flags = fetch_flags(w);
+    });
+    if (error_flags) *error_flags = flags;
+    if (s == WVB_OK && flags) {
+        set_last_error("simulation raised error flags 0x%x", flags);
+        s = WVB_ERR_SIM;
+    }
+    return s;
+}
+
+wvb_status wvb_wg_swap(wvb_wg* w) {
+    if (!w) return WVB_ERR_INVALID;
+    w->cur ^= 1;
+    return WVB_OK;
+}
+
+wvb_status wvb_wg_time_steps(wvb_wg* w, uint32_t n_steps, float* ms, int32_t* error_flags) {
+    if (!w || !ms) return WVB_ERR_INVALID;
+    int flags = 0;
+    wvb_status s = guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+        WVB_CUDA(cudaEventRecord(w->ev0, w->stream));
+        for (uint32_t i = 0; i < n_steps; ++i) enqueue_step(w);
+        WVB_CUDA(cudaEventRecord(w->ev1, w->stream));
+        WVB_CUDA(cudaEventSynchronize(w->ev1));
+        WVB_CUDA(cudaGetLastError());
+        WVB_CUDA(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+        flags = fetch_flags(w);
+    });
+    if (error_flags) *error_flags = flags;
+    if (s == WVB_OK && flags) s = WVB_ERR_SIM;
+    return s;
+}
+
+wvb_status wvb_wg_run(wvb_wg* w, const wvb_wg_run_params* p, uint32_t* steps_done,
+                      int32_t* error_flags) {
+    if (!w || !p || (p->n_steps && !p->signal) || (p->n_receivers && (!p->receiver_nodes || !p->out)))
+        return WVB_ERR_INVALID;
+    int flags = 0;
+    uint32_t done = 0;
+    wvb_status s = guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        dev_buf<double> d_signal, d_out;
+        dev_buf<long long> d_src, d_rcv;
+        d_signal.upload(p->signal, p->n_steps);
+        long long src_off = local_offset(w, p->source_node, nullptr);
+        const int n_src = src_off >= 0 ? 1 : 0;
+        d_src.upload(&src_off, 1);
+        std::vector<long long> roff(p->n_receivers);
+        for (uint32_t r = 0; r < p->n_receivers; ++r) {
+            int own = 0;
+            const long long o = local_offset(w, p->receiver_nodes[r], &own);
+            roff[r] = own ? o : -1;
+        }
+        if (p->n_receivers) {
+            d_rcv.upload(roff.data(), roff.size());
+            d_out.alloc((size_t)p->n_steps * p->n_receivers, true);
+        }
+        WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
+        for (uint32_t step = 0; step < p->n_steps; ++step) {
+            double* cur = w->P[w->cur].p;
+            if (n_src) {
+                wg_source<<<1, 32, 0, w->stream>>>(cur, d_src.p, n_src, d_signal.p, step, p->soft);
+                w->launches++;
+            }
+            if (p->n_receivers) {
+                wg_gather<<<(p->n_receivers + 127) / 128, 128, 0, w->stream>>>(
+                        cur, d_rcv.p, (int)p->n_receivers, d_out.p + (size_t)step * p->n_receivers);
+                w->launches++;
+            }
+            enqueue_step(w);
+            done = step + 1;
+            if (p->check_interval && (done % p->check_interval) == 0) {
+                flags = fetch_flags(w);
+                if (flags) break;
+            }
+        }
+        WVB_CUDA(cudaGetLastError());
+        if (!flags) flags = fetch_flags(w);
+        if (p->n_receivers) {
+            WVB_CUDA(cudaMemcpyAsync(p->out, d_out.p, (size_t)p->n_steps * p->n_receivers * 8,
+                                     cudaMemcpyDeviceToHost, w->stream));
+        }
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+    });
+    if (steps_done) *steps_done = done;
+    if (error_flags) *error_flags = flags;
+    if (s == WVB_OK && flags) {
+        set_last_error("simulation raised error flags 0x%x", flags);
+        s = WVB_ERR_SIM;
+    }
+    return s;
+}
+
+wvb_status wvb_wg_boundary_count(wvb_wg* w, int n_dims, uint64_t* count) {
+    if (!w || !count || n_dims < 1 || n_dims > 3) return WVB_ERR_INVALID;
+    *count = w->bl[n_dims - 1].n;
+    return WVB_OK;
+}
+
+wvb_status wvb_wg_read_boundary_data(wvb_wg* w, int N, wvb_boundary_data* out) {
+    if (!w || !out || N < 1 || N > 3) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        auto& l = w->bl[N - 1];
+        if (!l.n) return;
+        std::vector<double> mem((size_t)l.n * N * 6);
+        std::vector<uint32_t> ci((size_t)l.n * N);
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+        WVB_CUDA(cudaMemcpy(mem.data(), l.mem.p, mem.size() * 8, cudaMemcpyDeviceToHost));
+        WVB_CUDA(cudaMemcpy(ci.data(), l.ci.p, ci.size() * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t t = 0; t < l.n; ++t) {
+            for (int i = 0; i < N; ++i) {
+                wvb_boundary_data& b = out[(size_t)t * N + i];
+                for (int k = 0; k < 6; ++k) b.filter_memory[k] = mem[((size_t)i * 6 + k) * l.n + t];
+                b.coefficient_index = ci[(size_t)i * l.n + t];
+                b.pad_ = 0;
+            }
+        }
+    });
+}
+
+wvb_status wvb_wg_get_info(wvb_wg* w, wvb_wg_info* info) {
+    if (!w || !info) return WVB_ERR_INVALID;
+    memset(info, 0, sizeof *info);
+    info->local_nodes = (uint64_t)w->g.dx * w->g.dy * w->g.nzl;
+    info->air_nodes = w->air_nodes;
+    for (int k = 0; k < 3; ++k) info->boundary_nodes[k] = w->bl[k].n;
+    info->device_bytes = w->device_bytes;
+    info->kernel_launches = w->launches;
+    info->kernel_variant = w->variant;
+    info->tile[0] = w->variant == WVB_WG_KERNEL_TMA ? 128 : 64;
+    info->tile[1] = w->variant == WVB_WG_KERNEL_TMA ? w->ty : 8;
+    info->tile[2] = w->zchunks;
+    info->sm_count = w->sm_count;
+    return WVB_OK;
+}
+
+// Closed-form cuboid room; see the header for the layout. Layers per axis:
+// 0 and d-1 outside (id_none), 1 and d-2 the boundary shell, the rest inside.
+wvb_status wvb_mesh_cuboid(const int32_t dim[3], int32_t z0, int32_t nz, wvb_condensed_node* out,
+                           uint64_t counts[3]) {
+    if (!dim || dim[0] < 5 || dim[1] < 5 || dim[2] < 5) {
+        set_last_error("cuboid needs at least 5 nodes per axis");
+        return WVB_ERR_INVALID;
+    }
+    const int dx = dim[0], dy = dim[1], dz = dim[2];
+    if (z0 < 0 || nz < 0 || z0 + nz > dz || (nz && !out)) return WVB_ERR_INVALID;
+    const uint64_t nx = dx - 4, ny = dy - 4, nzz = dz - 4;
+    // class counts of one plane: shell plane (z = 1, dz-2) / interior plane
+    const uint64_t shell[3] = {nx * ny, 2 * (nx + ny), 4};
+    const uint64_t inner[3] = {2 * (nx + ny), 4, 0};
+    auto counts_before = [&](int z, uint64_t c[3]) {  // class counts in planes < z
+        for (int k = 0; k < 3; ++k) {
+            c[k] = 0;
+            if (z > 1) c[k] += shell[k];
+            if (z > 2) c[k] += inner[k] * (uint64_t)(std::min(z, dz - 2) - 2);
+            if (z > dz - 2) c[k] += shell[k];
+        }
+    };
+    if (counts) {
+        for (int k = 0; k < 3; ++k) counts[k] = 2 * shell[k] + inner[k] * nzz;
+    }
+    auto axis_bits = [](int c, int d, int neg_bit, int pos_bit, bool* outer) {
+        if (c == 0 || c == d - 1) { *outer = true; return 0; }
+        if (c == 1) return pos_bit;      // inner node lies on the + side
+        if (c == d - 2) return neg_bit;  // inner node lies on the - side
+        return 0;
+    };
+    parallel_for(nz, [&](int64_t i) {
+        const int z = z0 + (int)i;
+        uint64_t run[3];
+        counts_before(z, run);
+        wvb_condensed_node* pl = out + (size_t)i * dx * dy;
+        for (int y = 0; y < dy; ++y) {
+            for (int x = 0; x < dx; ++x) {
+                bool outer = false;
+                int bits = axis_bits(x, dx, WVB_ID_NX, WVB_ID_PX, &outer) |
+                           axis_bits(y, dy, WVB_ID_NY, WVB_ID_PY, &outer) |
+                           axis_bits(z, dz, WVB_ID_NZ, WVB_ID_PZ, &outer);
+                wvb_condensed_node n{0, 0};
+                if (!outer) {
+                    if (!bits) {
+                        n.boundary_type = WVB_ID_INSIDE;
+                    } else {
+                        n.boundary_type = bits;
+                        n.boundary_index = (uint32_t)run[__builtin_popcount(bits) - 1]++;
+                    }
+                }
+                pl[(size_t)y * dx + x] = n;
+            }
+        }
+    });
+    return WVB_OK;
+}
+
+}  // extern "C"
