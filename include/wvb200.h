@@ -208,6 +208,13 @@ wvb_status wvb_wg_read_boundary_data(wvb_wg* wg, int n_dims, wvb_boundary_data* 
 wvb_status wvb_wg_time_steps(wvb_wg* wg, uint32_t n_steps, float* milliseconds,
                              int32_t* error_flags);
 
+/* Times, each on its own, n back-to-back launches of (ms[0]) the air-node
+ * stencil kernel and (ms[1]) the three boundary kernels, with CUDA events on
+ * the launch stream. No swap and no exchange happens in between, so the
+ * memory traffic is that of a real step but the field is left in a state that
+ * is NOT a valid simulation state: call it last. Feeds bench.py's roofline. */
+wvb_status wvb_wg_time_kernels(wvb_wg* wg, uint32_t n, float ms[2]);
+
 /* introspection for bench / tests */
 typedef struct {
     uint64_t local_nodes;       /* owned nodes                                  */
@@ -232,7 +239,17 @@ wvb_status wvb_wg_get_info(wvb_wg* wg, wvb_wg_info* info);
 wvb_status wvb_mesh_cuboid(const int32_t dim[3], int32_t z0, int32_t nz,
                            wvb_condensed_node* nodes_out, uint64_t counts[3]);
 
+/* ---- test hooks ------------------------------------------------------------- */
+/* Device evaluation of the kernels' division-by-3 (FMA-corrected reciprocal
+ * multiply, csrc/wg_kernels.cuh third<true>) next to the IEEE `x / 3.0`, for n
+ * host doubles; the two outputs must be bit-identical. Runs on the current
+ * device. */
+wvb_status wvb_test_third(const double* in, size_t n, double* fast, double* ref);
+
 /* ---- misc ------------------------------------------------------------------ */
+/* Fills out[0..128) with a fresh ncclUniqueId (ncclGetUniqueId) for
+ * wvb_wg_desc.nccl_unique_id; rank 0 calls it and shares the bytes. */
+wvb_status wvb_nccl_unique_id(void* out, size_t size);
 int wvb_version(void);
 int wvb_device_count(void);
 /* text of the last failure on the calling thread ("" if none) */

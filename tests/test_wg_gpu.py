@@ -57,6 +57,33 @@ def run_both(omesh, steps, src, kernel, impulse=1.0):
 KERNELS = [("direct", _lib.KERNEL_DIRECT), ("tma", _lib.KERNEL_TMA)]
 
 
+def test_division_by_three_is_correctly_rounded():
+    """The kernels divide by 3 with an FMA-corrected reciprocal multiply
+    (csrc/wg_kernels.cuh third<true>); it must equal the IEEE division bit for
+    bit, including specials, the denormal range and adversarial significands."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    n = 1 << 24
+    bits = rng.integers(0, 1 << 52, n, dtype=np.uint64)
+    mode = np.arange(n) & 3
+    bits = np.where(mode == 1, np.uint64((1 << 52) - 1) - (bits & np.uint64(0xffff)), bits)  # ~all ones
+    bits = np.where(mode == 2, bits & np.uint64(0xfffff), bits)                             # ~power of two
+    exp = rng.integers(0, 2047, n, dtype=np.uint64)       # every exponent incl. denormals / inf / nan
+    exp = np.where(np.arange(n) % 5 == 0, exp, np.uint64(1023) + (exp % np.uint64(120)) - np.uint64(60))
+    sign = rng.integers(0, 2, n, dtype=np.uint64) << np.uint64(63)
+    x = (bits | (exp << np.uint64(52)) | sign).view(np.float64)
+    x[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1.7976931348623157e308, 3.0]
+    fast, ref = np.zeros(n), np.zeros(n)
+    _lib.check(_lib.lib().wvb_test_third(_lib.ptr(x), n, _lib.ptr(fast), _lib.ptr(ref)))
+    with np.errstate(all="ignore"):
+        host = x / 3.0
+    same = (fast.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(fast) & np.isnan(ref)) | \
+           ((fast == 0) & (ref == 0))
+    assert same.all(), "%d mismatches vs device division" % (~same).sum()
+    ok_host = (ref == host) | (np.isnan(ref) & np.isnan(host))
+    assert ok_host.all()
+
+
 @pytest.mark.parametrize("kname,kernel", KERNELS)
 @pytest.mark.parametrize("dims", [(140, 24, 14), (150, 37, 19), (133, 11, 9), (260, 20, 12)])
 def test_box_plaster_field_and_filters(dims, kname, kernel):

@@ -26,17 +26,24 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     m = wvb.cuboid_mesh(dims, [plaster()])
     nodes = dims[0] * dims[1] * dims[2]
-    configs = [("direct", None, None, z) for z in (0, 4, 16)]
-    for ty, st, zc in itertools.product((8, 16), (4, 5, 6), (0, 3, 7, 9, 16)):
-        if ty == 16 and st == 6:
+    configs = []
+    for div, pf, zc in itertools.product((1, 0), (4, 0, 8), (16, 8, 32)):
+        if div == 0 and pf == 8:
             continue
-        configs.append(("tma", ty, st, zc))
-    for kern, ty, st, zc in configs:
-        os.environ["WVB_WG_KERNEL"] = kern
-        os.environ["WVB_WG_ZCHUNKS"] = str(zc)
-        if ty:
-            os.environ["WVB_WG_TY"] = str(ty)
-            os.environ["WVB_WG_STAGES"] = str(st)
+        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=div, WVB_WG_PF=pf, WVB_WG_ZCHUNKS=zc))
+    for st, mb, zc in itertools.product((5, 4), (1, 4), (12, 16, 24)):
+        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=st, WVB_WG_MINB=mb, WVB_WG_ZCHUNKS=zc,
+                            WVB_WG_DIV=1))
+    configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
+                        WVB_WG_DIV=0))
+    only = os.environ.get("SWEEP_ONLY")
+    for cfg in configs:
+        if only and cfg["WVB_WG_KERNEL"] != only:
+            continue
+        for k, v in cfg.items():
+            os.environ[k] = str(v)
+        kern = cfg["WVB_WG_KERNEL"]
+        tag = " ".join("%s=%s" % (k[7:].lower(), v) for k, v in cfg.items() if k != "WVB_WG_KERNEL")
         try:
             with wvb.Waveguide(m) as g:
                 g.write(m.index(dims[0] // 2, dims[1] // 2, dims[2] // 2), 1.0)
@@ -44,11 +51,10 @@ def main():
                 best = min(g.time_steps(steps)[0] for _ in range(3))
                 info = g.info()
             ms = best / steps
-            print("%-6s ty=%s st=%s zc=%-3d | %.4f ms/step  %8.1f Mnode/s  %7.1f GB/s@32B  tile=%s" %
-                  (kern, ty, st, info["tile"][2], ms, nodes / ms / 1e3, nodes * 32 / ms / 1e6, info["tile"]),
-                  flush=True)
+            print("%-6s %-40s | %.4f ms/step  %8.1f Mnode/s  %7.1f GB/s@32B  tile=%s" %
+                  (kern, tag, ms, nodes / ms / 1e3, nodes * 32 / ms / 1e6, info["tile"]), flush=True)
         except Exception as e:  # noqa: BLE001
-            print(kern, ty, st, zc, "FAILED", e, flush=True)
+            print(kern, tag, "FAILED", e, flush=True)
 
 
 if __name__ == "__main__":

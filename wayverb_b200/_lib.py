@@ -68,7 +68,8 @@ WG_SYMBOLS = [
     "wvb_wg_create", "wvb_wg_destroy", "wvb_wg_write_f64", "wvb_wg_read_f64", "wvb_wg_read_field",
     "wvb_wg_read_field_f32", "wvb_wg_write_field", "wvb_wg_step", "wvb_wg_launch", "wvb_wg_swap",
     "wvb_wg_run",
-    "wvb_wg_boundary_count", "wvb_wg_read_boundary_data", "wvb_wg_time_steps", "wvb_wg_get_info",
+    "wvb_wg_boundary_count", "wvb_wg_read_boundary_data", "wvb_wg_time_steps", "wvb_wg_time_kernels",
+    "wvb_wg_get_info", "wvb_nccl_unique_id", "wvb_test_third",
     "wvb_mesh_cuboid", "wvb_version", "wvb_device_count", "wvb_last_error",
 ]
 
@@ -109,6 +110,9 @@ def lib():
     L.wvb_wg_boundary_count.argtypes = [vp, C.c_int, C.POINTER(u64)]
     L.wvb_wg_read_boundary_data.argtypes = [vp, C.c_int, vp]
     L.wvb_wg_time_steps.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.wvb_wg_time_kernels.argtypes = [vp, u32, C.POINTER(C.c_float * 2)]
+    L.wvb_test_third.argtypes = [vp, C.c_size_t, vp, vp]
+    L.wvb_nccl_unique_id.argtypes = [vp, C.c_size_t]
     L.wvb_wg_get_info.argtypes = [vp, C.POINTER(WgInfo)]
     L.wvb_mesh_cuboid.argtypes = [C.POINTER(i32 * 3), i32, i32, vp, C.POINTER(u64 * 3)]
     _lib = L

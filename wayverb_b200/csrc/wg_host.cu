@@ -95,6 +95,7 @@ struct wvb_wg {
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
     int ty = 8, nstage = 5, zchunks = 1;
+    int fast_div = 1, pf = 4, minb = 1;
     int sm_count = 0;
     nccl::comm_t comm = nullptr;
     size_t device_bytes = 0;
@@ -255,23 +256,48 @@ void launch_tma(wvb_wg* w, const double* cur, double* prev) {
             w->map[w->cur], cur, prev, w->code.p, g, w->zchunks, w->flag.p);
 }
 
-void launch_air(wvb_wg* w, const double* cur, double* prev) {
+// the TMA configurations that are compiled in: (TY, stages, fast division, min CTAs/SM)
+#define WVB_TMA_CONFIGS(X) \
+    X(8, 5, true, 1)       \
+    X(8, 5, false, 1)      \
+    X(8, 5, true, 4)       \
+    X(8, 4, true, 1)       \
+    X(8, 4, true, 4)       \
+    X(8, 6, true, 1)       \
+    X(16, 5, true, 1)
+
+template <class F>
+bool with_tma_cfg(const wvb_wg* w, F&& f) {
+#define X(TY, NS, FD, MB)                                                               \
+    if (w->ty == TY && w->nstage == NS && (w->fast_div != 0) == FD && w->minb == MB) { \
+        f(TmaCfg<TY, NS, FD, MB>{});                                                    \
+        return true;                                                                    \
+    }
+    WVB_TMA_CONFIGS(X)
+#undef X
+    return false;
+}
+
+template <bool FD, int PF>
+void launch_direct_t(wvb_wg* w, const double* cur, double* prev) {
     const WgGeom& g = w->g;
+    constexpr int BX = 32, BY = 8;
+    const int zchunk = (g.nzl + w->zchunks - 1) / w->zchunks;
+    dim3 grid(((g.dx + 1) / 2 + BX - 1) / BX, (g.dy + BY - 1) / BY, (g.nzl + zchunk - 1) / zchunk);
+    wg_air_direct<BX, BY, FD, PF><<<grid, dim3(BX, BY), 0, w->stream>>>(cur, prev, w->code.p, g,
+                                                                         zchunk, w->flag.p);
+}
+
+void launch_air(wvb_wg* w, const double* cur, double* prev) {
     if (w->variant == WVB_WG_KERNEL_TMA) {
-        if (w->ty == 16) {
-            if (w->nstage == 4) launch_tma<TmaCfg<16, 4>>(w, cur, prev);
-            else launch_tma<TmaCfg<16, 5>>(w, cur, prev);
-        } else {
-            if (w->nstage == 4) launch_tma<TmaCfg<8, 4>>(w, cur, prev);
-            else if (w->nstage == 6) launch_tma<TmaCfg<8, 6>>(w, cur, prev);
-            else launch_tma<TmaCfg<8, 5>>(w, cur, prev);
-        }
+        with_tma_cfg(w, [&](auto cfg) { launch_tma<decltype(cfg)>(w, cur, prev); });
+    } else if (w->fast_div) {
+        if (w->pf == 0) launch_direct_t<true, 0>(w, cur, prev);
+        else if (w->pf == 8) launch_direct_t<true, 8>(w, cur, prev);
+        else launch_direct_t<true, 4>(w, cur, prev);
     } else {
-        constexpr int BX = 32, BY = 8;
-        const int zchunk = (g.nzl + w->zchunks - 1) / w->zchunks;
-        dim3 grid(((g.dx + 1) / 2 + BX - 1) / BX, (g.dy + BY - 1) / BY, (g.nzl + zchunk - 1) / zchunk);
-        wg_air_direct<BX, BY><<<grid, dim3(BX, BY), 0, w->stream>>>(cur, prev, w->code.p, g, zchunk,
-                                                                     w->flag.p);
+        if (w->pf == 0) launch_direct_t<false, 0>(w, cur, prev);
+        else launch_direct_t<false, 4>(w, cur, prev);
     }
     w->launches++;
 }
@@ -518,27 +544,32 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->variant = want;
     w->ty = env_int("WVB_WG_TY", ((d->flags >> 8) & 0xff) ? ((d->flags >> 8) & 0xff) : 8);
     w->nstage = env_int("WVB_WG_STAGES", 5);
-    if (w->ty != 16) w->ty = 8;
-    if (w->ty == 16 && w->nstage != 4) w->nstage = 5;
-    if (w->nstage != 4 && w->nstage != 6) w->nstage = 5;
+    w->fast_div = env_int("WVB_WG_DIV", 1) ? 1 : 0;
+    w->pf = env_int("WVB_WG_PF", 4);
+    w->minb = env_int("WVB_WG_MINB", 1);
     int slots;
     long long tiles;
     if (w->variant == WVB_WG_KERNEL_TMA) {
-        set_tma_attr<TmaCfg<8, 4>>();
-        set_tma_attr<TmaCfg<8, 5>>();
-        set_tma_attr<TmaCfg<8, 6>>();
-        set_tma_attr<TmaCfg<16, 4>>();
-        set_tma_attr<TmaCfg<16, 5>>();
+        int occ = 0;
+        const bool known = with_tma_cfg(w, [&](auto cfg) {
+            using Cfg = decltype(cfg);
+            set_tma_attr<Cfg>();
+            occ = tma_occupancy<Cfg>();
+        });
+        if (!known) {  // unknown combination: fall back to the default configuration
+            w->ty = 8; w->nstage = 5; w->fast_div = 1; w->minb = 1;
+            with_tma_cfg(w, [&](auto cfg) {
+                using Cfg = decltype(cfg);
+                set_tma_attr<Cfg>();
+                occ = tma_occupancy<Cfg>();
+            });
+        }
         make_tensor_map(w, 0, w->ty);
         make_tensor_map(w, 1, w->ty);
-        int occ;
-        if (w->ty == 16) occ = w->nstage == 4 ? tma_occupancy<TmaCfg<16, 4>>() : tma_occupancy<TmaCfg<16, 5>>();
-        else occ = w->nstage == 4 ? tma_occupancy<TmaCfg<8, 4>>()
-                 : w->nstage == 6 ? tma_occupancy<TmaCfg<8, 6>>() : tma_occupancy<TmaCfg<8, 5>>();
         slots = std::max(1, occ) * w->sm_count;
         tiles = (long long)((dx + 127) / 128) * ((dy + w->ty - 1) / w->ty);
     } else {
-        slots = 8 * w->sm_count;
+        slots = 4 * w->sm_count;
         tiles = (long long)(((dx + 1) / 2 + 31) / 32) * ((dy + 7) / 8);
     }
     const int zc_req = env_int("WVB_WG_ZCHUNKS", (int)((d->flags >> 16) & 0xfff));
@@ -730,6 +761,55 @@ wvb_status wvb_wg_time_steps(wvb_wg* w, uint32_t n_steps, float* ms, int32_t* er
     if (error_flags) *error_flags = flags;
     if (s == WVB_OK && flags) s = WVB_ERR_SIM;
     return s;
+}
+
+wvb_status wvb_wg_time_kernels(wvb_wg* w, uint32_t n, float ms[2]) {
+    if (!w || !ms) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(w->dev));
+        const double* cur = w->P[w->cur].p;
+        double* prev = w->P[w->cur ^ 1].p;
+        WVB_CUDA(cudaStreamSynchronize(w->stream));
+        WVB_CUDA(cudaEventRecord(w->ev0, w->stream));
+        for (uint32_t i = 0; i < n; ++i) launch_air(w, cur, prev);
+        WVB_CUDA(cudaEventRecord(w->ev1, w->stream));
+        WVB_CUDA(cudaEventSynchronize(w->ev1));
+        WVB_CUDA(cudaEventElapsedTime(&ms[0], w->ev0, w->ev1));
+        WVB_CUDA(cudaEventRecord(w->ev0, w->stream));
+        for (uint32_t i = 0; i < n; ++i) {
+            launch_boundary<1>(w, cur, prev);
+            launch_boundary<2>(w, cur, prev);
+            launch_boundary<3>(w, cur, prev);
+        }
+        WVB_CUDA(cudaEventRecord(w->ev1, w->stream));
+        WVB_CUDA(cudaEventSynchronize(w->ev1));
+        WVB_CUDA(cudaEventElapsedTime(&ms[1], w->ev0, w->ev1));
+        WVB_CUDA(cudaGetLastError());
+    });
+}
+
+wvb_status wvb_test_third(const double* in, size_t n, double* fast, double* ref) {
+    if (!in || !fast || !ref) return WVB_ERR_INVALID;
+    return guarded([&] {
+        dev_buf<double> a, b, c;
+        a.upload(in, n);
+        b.alloc(n, false);
+        c.alloc(n, false);
+        wg_third_test<<<(unsigned)((n + 255) / 256), 256>>>(a.p, b.p, c.p, n);
+        WVB_CUDA(cudaGetLastError());
+        WVB_CUDA(cudaMemcpy(fast, b.p, n * 8, cudaMemcpyDeviceToHost));
+        WVB_CUDA(cudaMemcpy(ref, c.p, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+wvb_status wvb_nccl_unique_id(void* out, size_t size) {
+    if (!out || size < sizeof(nccl::unique_id)) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_REQUIRE(nccl::get().ok, WVB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+        nccl::unique_id id;
+        nccl_check(nccl::get().GetUniqueId(&id), "ncclGetUniqueId");
+        memcpy(out, &id, sizeof id);
+    });
 }
 
 wvb_status wvb_wg_run(wvb_wg* w, const wvb_wg_run_params* p, uint32_t* steps_done,

@@ -68,9 +68,32 @@ __device__ __forceinline__ void st2(double* p, double2 v) {
     *reinterpret_cast<double2*>(p) = v;
 }
 
+// x / 3.0, correctly rounded, without the generic division sequence.
+// q = RN(x * RN(1/3)) is a faithful rounding of x/3 (RN(1/3) = (1/3)(1 - 2^-54), so
+// the product is 0.25..0.5 ulp low before its own half-ulp rounding); with the
+// exact residual r = x - 3q (one FMA) Markstein's theorem gives
+// RN(q + r * RN(1/3)) == RN(x / 3). Valid while nothing under/overflows, so the
+// fast path is taken for 2^-900 <= |x| < 2^900 and for x == 0; everything else
+// (inf, nan, denormal range) takes the true division. tests/test_wg_gpu.py
+// checks bit-equality with `/ 3.0` on 2^26 adversarial inputs.
+template <bool FAST>
+__device__ __forceinline__ double third(double x) {
+    if (!FAST) return x / 3.0;
+    const double z = 0x1.5555555555555p-2;
+    const double q = x * z;
+    const double r = __fma_rn(-3.0, q, x);
+    double q2 = __fma_rn(r, z, q);
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    const bool ok = (e - 123u < 1800u) || (((hi << 1) | (unsigned)__double2loint(x)) == 0u);
+    if (!ok) q2 = x / 3.0;
+    return q2;
+}
+
 // normal_waveguide_update with off-mesh ports contributing 0 (x + 0.0 == x).
-// Summation order nx, px, ny, py, nz, pz and a true division by 3, exactly as
-// program.cpp:402-410.
+// Summation order nx, px, ny, py, nz, pz and a correctly rounded division by 3,
+// exactly as program.cpp:402-410.
+template <bool FAST = true>
 __device__ __forceinline__ double air_update(double nx, double px, double ny, double py,
                                              double nz, double pz, double prev) {
     double r = 0.0;
@@ -80,9 +103,13 @@ __device__ __forceinline__ double air_update(double nx, double px, double ny, do
     r += py;
     r += nz;
     r += pz;
-    r /= 3.0;
+    r = third<FAST>(r);
     r -= prev;
     return r;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 __device__ __forceinline__ int classify_bad(double v) {
@@ -102,7 +129,7 @@ __device__ __forceinline__ void raise_flags(int bad, int* flag) {
 // neighbours come through L1. Bring-up kernel and cross-check for the TMA one.
 // grid = (ceil(dx/2/BX), ceil(dy/BY), zchunks), block = (BX, BY).
 // ---------------------------------------------------------------------------
-template <int BX, int BY>
+template <int BX, int BY, bool FAST_DIV, int PF>
 __global__ void __launch_bounds__(BX* BY)
 wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
               const uint8_t* __restrict__ code, WgGeom g, int zchunk, int* __restrict__ flag) {
@@ -112,7 +139,7 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
     const int zs = 1 + blockIdx.z * zchunk;
     const int ze = min(zs + zchunk, g.nzl + 1);
     int bad = 0;
-    if (active) {
+    if (active && zs < ze) {
         const bool has1 = x0 + 1 < g.dx;
         const bool hasL = x0 > 0, hasR = x0 + 2 < g.dx;
         const bool hasU = y > 0, hasD = y + 1 < g.dy;
@@ -120,17 +147,31 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
         long long coff = ((long long)zs * g.dy + y) * g.pc + x0;
         double2 below = ld2(cur + off - g.plane);
         double2 mid = ld2(cur + off);
+        double2 above = ld2(cur + off + g.plane);
+        double2 p = ld2(prev + off);
+        uchar2 c = *reinterpret_cast<const uchar2*>(code + coff);
         for (int z = zs; z < ze; ++z, off += g.plane, coff += g.cplane) {
-            const double2 above = ld2(cur + off + g.plane);
+            // the three streaming operands of the NEXT iteration are requested
+            // before this iteration's arithmetic (software pipelining) ...
+            double2 above_n = make_double2(0.0, 0.0), p_n = make_double2(0.0, 0.0);
+            uchar2 c_n = make_uchar2(0, 0);
+            if (z + 1 < ze) {
+                above_n = ld2(cur + off + 2 * g.plane);
+                p_n = ld2(prev + off + g.plane);
+                c_n = *reinterpret_cast<const uchar2*>(code + coff + g.cplane);
+            }
+            // ... and the planes PF iterations ahead are pulled into L2
+            if (PF > 0 && z + PF <= g.nzl) {
+                prefetch_l2(cur + off + (long long)(PF + 1) * g.plane);
+                prefetch_l2(prev + off + (long long)PF * g.plane);
+            }
             const double l = hasL ? cur[off - 1] : 0.0;
             const double r = hasR ? cur[off + 2] : 0.0;
             const double2 u = hasU ? ld2(cur + off - g.px) : make_double2(0.0, 0.0);
             const double2 d = hasD ? ld2(cur + off + g.px) : make_double2(0.0, 0.0);
-            const double2 p = ld2(prev + off);
-            const uchar2 c = *reinterpret_cast<const uchar2*>(code + coff);
             const double right0 = has1 ? mid.y : 0.0;
-            double v0 = air_update(l, right0, u.x, d.x, below.x, above.x, p.x);
-            double v1 = air_update(mid.x, r, u.y, d.y, below.y, above.y, p.y);
+            double v0 = air_update<FAST_DIV>(l, right0, u.x, d.x, below.x, above.x, p.x);
+            double v1 = air_update<FAST_DIV>(mid.x, r, u.y, d.y, below.y, above.y, p.y);
             if (c.x != CLS_AIR) v0 = 0.0;
             if (c.y != CLS_AIR) v1 = 0.0;
             const bool w0 = c.x != CLS_BOUNDARY;
@@ -145,9 +186,22 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
             }
             below = mid;
             mid = above;
+            above = above_n;
+            p = p_n;
+            c = c_n;
         }
     }
     raise_flags(bad, flag);
+}
+
+// test hook: out[i] = third<true>(in[i]) and ref[i] = in[i] / 3.0
+__global__ void wg_third_test(const double* __restrict__ in, double* __restrict__ fast,
+                              double* __restrict__ ref, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        fast[i] = third<true>(in[i]);
+        ref[i] = in[i] / 3.0;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -206,8 +260,10 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
 
 }  // namespace tma
 
-template <int TY_, int NSTAGE_>
+template <int TY_, int NSTAGE_, bool FAST_DIV_ = true, int MINB_ = 1>
 struct TmaCfg {
+    static constexpr bool FAST_DIV = FAST_DIV_;
+    static constexpr int MINB = MINB_;
     static constexpr int TX = 128;
     static constexpr int TY = TY_;
     static constexpr int NSTAGE = NSTAGE_;
@@ -224,7 +280,7 @@ struct TmaCfg {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 wg_air_tma(const __grid_constant__ CUtensorMap cur_map, const double* __restrict__ /*cur*/,
            double* __restrict__ prev, const uint8_t* __restrict__ code, WgGeom g, int zchunks,
            int* __restrict__ flag) {
@@ -323,8 +379,8 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, const double* __restrict
             const double2 d = ld2(sm + o + BOXX);
             const double2 below = ld2(sb + o);
             const double2 above = ld2(sa + o);
-            double v0 = air_update(l, mid.y, u.x, d.x, below.x, above.x, p[rr].x);
-            double v1 = air_update(mid.x, rgt, u.y, d.y, below.y, above.y, p[rr].y);
+            double v0 = air_update<Cfg::FAST_DIV>(l, mid.y, u.x, d.x, below.x, above.x, p[rr].x);
+            double v1 = air_update<Cfg::FAST_DIV>(mid.x, rgt, u.y, d.y, below.y, above.y, p[rr].y);
             if (c[rr].x != CLS_AIR) v0 = 0.0;
             if (c[rr].y != CLS_AIR) v1 = 0.0;
             const bool inb = xin && y < g.dy;

@@ -101,6 +101,13 @@ def cuboid_mesh(dims, coeffs, z0=0, nz=None) -> Mesh:
                 np.zeros((counts[2], 3), np.uint32), nodes_z0=z0)
 
 
+def nccl_unique_id() -> bytes:
+    """128 bytes of a fresh ncclUniqueId (rank 0 creates, everybody gets a copy)."""
+    buf = C.create_string_buffer(128)
+    check(lib().wvb_nccl_unique_id(buf, 128))
+    return buf.raw
+
+
 class Waveguide:
     """One `wvb_wg` handle: a z-slab of the mesh on one GPU."""
 
@@ -198,6 +205,12 @@ class Waveguide:
         ms, f = C.c_float(), C.c_int32()
         check(lib().wvb_wg_time_steps(self._h, int(n), C.byref(ms), C.byref(f)), allow_sim=True)
         return ms.value, f.value
+
+    def time_kernels(self, n):
+        """(air kernel ms, boundary kernels ms) for n launches each; invalidates the field."""
+        ms = (C.c_float * 2)()
+        check(lib().wvb_wg_time_kernels(self._h, int(n), C.byref(ms)))
+        return float(ms[0]), float(ms[1])
 
     def run_device(self, src_node, signal, rcv_nodes, soft=False, check_interval=0):
         """wvb_wg_run: the stock hard/soft source + node receivers on the device."""
