@@ -238,7 +238,9 @@ void make_tensor_map(wvb_wg* w, int which, int ty) {
     encode_tiled_fn enc = get_encode_tiled();
     WVB_REQUIRE(enc != nullptr, WVB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     const WgGeom& g = w->g;
-    cuuint64_t gdim[3] = {(cuuint64_t)g.dx, (cuuint64_t)g.dy, (cuuint64_t)(g.nzl + 2)};
+    // the whole padded array (zero border included) is the tensor; boxes that
+    // overhang it are zero-filled by the TMA unit
+    cuuint64_t gdim[3] = {(cuuint64_t)g.px, (cuuint64_t)g.py, (cuuint64_t)(g.nzl + 2)};
     cuuint64_t gstr[2] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.plane * 8};
     cuuint32_t box[3] = {132, (cuuint32_t)(ty + 2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -252,8 +254,9 @@ template <class Cfg>
 void launch_tma(wvb_wg* w, const double* cur, double* prev) {
     const WgGeom& g = w->g;
     dim3 grid((g.dx + Cfg::TX - 1) / Cfg::TX, (g.dy + Cfg::TY - 1) / Cfg::TY, w->zchunks);
+    (void)cur;  // read through the tensor map of P[w->cur]
     wg_air_tma<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
-            w->map[w->cur], cur, prev, w->code.p, g, w->zchunks, w->flag.p);
+            w->map[w->cur], prev, w->code.p, g, w->zchunks, w->flag.p);
 }
 
 // the TMA configurations that are compiled in: (TY, stages, fast division, min CTAs/SM)
@@ -387,7 +390,7 @@ long long local_offset(const wvb_wg* w, uint64_t node, int* owned) {
     const long long lz = z - w->z_begin + 1;
     if (lz < 0 || lz > w->g.nzl + 1) return -1;
     if (owned) *owned = (lz >= 1 && lz <= w->g.nzl);
-    return (lz * w->g.dy + y) * w->g.px + x;
+    return wg_offset(w->g, x, y, lz);
 }
 
 void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
@@ -431,16 +434,17 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
 
     WgGeom& g = w->g;
     g.dx = dx; g.dy = dy; g.nzl = d->z_end - d->z_begin;
-    g.px = (dx + 1) & ~1;
-    g.pc = (dx + 15) & ~15;
-    g.plane = (long long)g.px * dy;
+    g.px = (dx + WG_XO + 2 + 3) & ~3;  // zero border: WG_XO columns left, >= 2 right
+    g.py = dy + 2;                     // zero rows above and below
+    g.pc = (dx + 1 + 15) & ~15;        // class bytes: >= 1 "do not write" column right of the row
+    g.plane = (long long)g.px * g.py;
     g.cplane = (long long)g.pc * dy;
     const long long total = g.plane * (g.nzl + 2);
     WVB_REQUIRE(total < 0xffffffffll, WVB_ERR_UNSUPPORTED, "slab too large for 32-bit offsets");
 
     // ---- digest the nodes: class bytes + boundary lists (node order) ----------
     const node_view nv{d->nodes, d->nodes_z0, d->nodes_nz, dx, dy, dz};
-    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), CLS_NONE);
+    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), CLS_BOUNDARY);
     std::vector<std::array<uint32_t, 3>> plane_counts(g.nzl);
     std::vector<uint64_t> plane_air(g.nzl, 0);
     parallel_for(g.nzl, [&](int64_t lp) {
@@ -488,7 +492,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
                 if (node_class(nd.boundary_type, &N) != CLS_BOUNDARY) continue;
                 const int k = N - 1;
                 const uint32_t t = pos[k]++;
-                hl[k].off[t] = (uint32_t)(((long long)(lp + 1) * dy + y) * g.px + x);
+                hl[k].off[t] = (uint32_t)wg_offset(g, x, y, lp + 1);
                 hl[k].meta[t] = analyse_boundary_node(nv, x, y, z, nd.boundary_type, N);
                 hl[k].bidx[t] = nd.boundary_index;
                 const uint64_t rel = (uint64_t)nd.boundary_index - d->index_base[k];
@@ -660,14 +664,34 @@ wvb_status wvb_wg_read_f64(wvb_wg* w, uint64_t node, double* value, int* owned) 
     });
 }
 
+// dense (x fastest) <-> padded device planes, owned planes only
+static void copy_field(wvb_wg* w, double* dev, double* host_out, const double* host_in) {
+    const WgGeom& g = w->g;
+    cudaMemcpy3DParms p = {};
+    const cudaPitchedPtr dptr =
+            make_cudaPitchedPtr(dev, (size_t)g.px * 8, (size_t)g.px, (size_t)g.py);
+    const cudaPos dpos = make_cudaPos((size_t)WG_XO * 8, 1, 1);
+    p.extent = make_cudaExtent((size_t)g.dx * 8, (size_t)g.dy, (size_t)g.nzl);
+    if (host_out) {
+        p.srcPtr = dptr;
+        p.srcPos = dpos;
+        p.dstPtr = make_cudaPitchedPtr(host_out, (size_t)g.dx * 8, (size_t)g.dx, (size_t)g.dy);
+        p.kind = cudaMemcpyDeviceToHost;
+    } else {
+        p.srcPtr = make_cudaPitchedPtr(const_cast<double*>(host_in), (size_t)g.dx * 8, (size_t)g.dx,
+                                       (size_t)g.dy);
+        p.dstPtr = dptr;
+        p.dstPos = dpos;
+        p.kind = cudaMemcpyHostToDevice;
+    }
+    WVB_CUDA(cudaMemcpy3DAsync(&p, w->stream));
+}
+
 wvb_status wvb_wg_read_field(wvb_wg* w, double* out) {
     if (!w || !out) return WVB_ERR_INVALID;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
-        const WgGeom& g = w->g;
-        WVB_CUDA(cudaMemcpy2DAsync(out, (size_t)g.dx * 8, w->P[w->cur].p + g.plane, (size_t)g.px * 8,
-                                   (size_t)g.dx * 8, (size_t)g.dy * g.nzl, cudaMemcpyDeviceToHost,
-                                   w->stream));
+        copy_field(w, w->P[w->cur].p, out, nullptr);
         WVB_CUDA(cudaStreamSynchronize(w->stream));
     });
 }
@@ -691,11 +715,8 @@ wvb_status wvb_wg_write_field(wvb_wg* w, const double* in) {
     if (!w || !in) return WVB_ERR_INVALID;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
-        const WgGeom& g = w->g;
         double* cur = w->P[w->cur].p;
-        WVB_CUDA(cudaMemcpy2DAsync(cur + g.plane, (size_t)g.px * 8, in, (size_t)g.dx * 8,
-                                   (size_t)g.dx * 8, (size_t)g.dy * g.nzl, cudaMemcpyHostToDevice,
-                                   w->stream));
+        copy_field(w, cur, nullptr, in);
         exchange_ghosts(w, cur);
         WVB_CUDA(cudaStreamSynchronize(w->stream));
     });

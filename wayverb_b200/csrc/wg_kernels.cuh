@@ -13,14 +13,21 @@
 //                  node-ordered lists with SoA filter state.
 //
 // Arithmetic is fp64 throughout and keeps the reference's operation order
-// (compiled with -fmad=false), so results are bit-identical to the oracle's
-// Real=double mode, not merely within 1e-10.
+// (compiled with -fmad=false; the only FMAs are the explicit ones of the exact
+// division by 3), so results are bit-identical to the oracle's Real=double
+// mode, not merely within 1e-10.
 //
 // Device layout (per handle, per GPU):
-//   P[2]   fp64 pressures, (nzl+2) planes x dy rows x px doubles; plane 0 and
-//          nzl+1 are ghost planes (neighbour slab or off-mesh = 0); px = dx
-//          rounded up to even so rows are 16-byte aligned.
-//   code   u8 node class, same plane/row order, pitch pc (multiple of 16).
+//   P[2]   fp64 pressures, (nzl+2) planes x (dy+2) rows x px doubles.
+//          Plane 0 and nzl+1 are ghost planes (neighbour slab, or zero at the
+//          mesh ends); row 0 and dy+1 of every plane and the columns left of
+//          WG_XO / right of WG_XO+dx are a zero border that is never written.
+//          An off-mesh port therefore reads 0.0 and "skip off-mesh ports"
+//          (program.cpp:402-407) needs no bounds test. Node (x, y, local plane
+//          lz) lives at ((lz*(dy+2) + y+1)*px + WG_XO + x); WG_XO = 4 and px a
+//          multiple of 4 keep node pairs 16-byte and rows 32-byte aligned.
+//   code   u8 node class, (nzl+2) x dy x pc bytes (no border); columns >= dx of
+//          a row are CLS_BOUNDARY ("do not write").
 //   lists  per boundary class N: off[n] (element offset into P), meta[n],
 //          ci[N][n] coefficient indices, mem[N][6][n] filter memory.
 #pragma once
@@ -35,12 +42,19 @@ namespace wvb {
 
 enum : uint8_t { CLS_NONE = 0, CLS_AIR = 1, CLS_BOUNDARY = 2 };
 
+constexpr int WG_XO = 4;  // zero columns left of x = 0
+
 struct WgGeom {
-    int dx, dy, nzl;  // owned planes are local planes 1..nzl
-    int px, pc;       // row pitches of P (doubles) and code (bytes)
-    long long plane;  // px * dy
-    long long cplane; // pc * dy
+    int dx, dy, nzl;   // owned planes are local planes 1..nzl
+    int px, py;        // row pitch (doubles) and rows per plane (dy + 2)
+    int pc;            // row pitch of the class bytes
+    long long plane;   // px * py   (elements)
+    long long cplane;  // pc * dy   (bytes)
 };
+
+__host__ __device__ inline long long wg_offset(const WgGeom& g, int x, int y, long long lz) {
+    return (lz * g.py + y + 1) * g.px + WG_XO + x;
+}
 
 // meta word of a boundary-list entry
 //  [0:3) [3:6) [6:9)  inner ports 0..5 (nx,px,ny,py,nz,pz) or 6 = "-1" (self)
@@ -67,49 +81,32 @@ __device__ __forceinline__ double2 ld2(const double* p) {
 __device__ __forceinline__ void st2(double* p, double2 v) {
     *reinterpret_cast<double2*>(p) = v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // x / 3.0, correctly rounded, without the generic division sequence.
 // q = RN(x * RN(1/3)) is a faithful rounding of x/3 (RN(1/3) = (1/3)(1 - 2^-54), so
 // the product is 0.25..0.5 ulp low before its own half-ulp rounding); with the
-// exact residual r = x - 3q (one FMA) Markstein's theorem gives
-// RN(q + r * RN(1/3)) == RN(x / 3). Valid while nothing under/overflows, so the
-// fast path is taken for 2^-900 <= |x| < 2^900 and for x == 0; everything else
-// (inf, nan, denormal range) takes the true division. tests/test_wg_gpu.py
-// checks bit-equality with `/ 3.0` on 2^26 adversarial inputs.
-template <bool FAST>
-__device__ __forceinline__ double third(double x) {
-    if (!FAST) return x / 3.0;
+// exact residual r = x - 3q (one FMA; representable for every finite x, also
+// in the denormal range) Markstein's theorem gives RN(q + r * RN(1/3)) ==
+// RN(x / 3): x/3 in units of the result's ulp has fractional part 0, 1/3 or
+// 2/3, never within 1/6 ulp of a rounding boundary, while r*RN(1/3) differs
+// from r/3 by a relative 2^-54. So the identity holds for EVERY finite double;
+// only x = +-inf gives NaN instead of inf. Callers therefore re-evaluate with
+// slow_third() in the (rare) branch that handles non-finite results.
+// tests/test_wg_gpu.py checks bit-equality with `/ 3.0` on 2^24 adversarial inputs.
+__device__ __forceinline__ double fast_third(double x) {
     const double z = 0x1.5555555555555p-2;
     const double q = x * z;
     const double r = __fma_rn(-3.0, q, x);
-    double q2 = __fma_rn(r, z, q);
-    const unsigned hi = (unsigned)__double2hiint(x);
-    const unsigned e = (hi >> 20) & 0x7ffu;
-    const bool ok = (e - 123u < 1800u) || (((hi << 1) | (unsigned)__double2loint(x)) == 0u);
-    if (!ok) q2 = x / 3.0;
-    return q2;
+    return __fma_rn(r, z, q);
 }
+__device__ __noinline__ double slow_third(double x) { return x / 3.0; }
 
-// normal_waveguide_update with off-mesh ports contributing 0 (x + 0.0 == x).
-// Summation order nx, px, ny, py, nz, pz and a correctly rounded division by 3,
-// exactly as program.cpp:402-410.
-template <bool FAST = true>
-__device__ __forceinline__ double air_update(double nx, double px, double ny, double py,
-                                             double nz, double pz, double prev) {
-    double r = 0.0;
-    r += nx;
-    r += px;
-    r += ny;
-    r += py;
-    r += nz;
-    r += pz;
-    r = third<FAST>(r);
-    r -= prev;
-    return r;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+// |v|'s high word: >= 0x7ff00000 iff v is inf or nan
+__device__ __forceinline__ unsigned abs_hi(double v) {
+    return (unsigned)__double2hiint(v) & 0x7fffffffu;
 }
 
 __device__ __forceinline__ int classify_bad(double v) {
@@ -124,9 +121,47 @@ __device__ __forceinline__ void raise_flags(int bad, int* flag) {
     }
 }
 
+// The update of one x-adjacent node pair (normal_waveguide_update,
+// program.cpp:393-412, for both nodes). Port order nx, px, ny, py, nz, pz; the
+// leading `0 +` of the reference is the first operand itself. `ck` holds the two
+// class bytes. Writes the result(s) to dst unless the class says BOUNDARY.
+template <bool FAST_DIV>
+__device__ __forceinline__ void update_pair(double l, double2 mid, double r, double2 u, double2 d,
+                                            double2 below, double2 above, double2 p, unsigned ck,
+                                            double* __restrict__ dst, int& bad) {
+    const double s0 = ((((l + mid.y) + u.x) + d.x) + below.x) + above.x;
+    const double s1 = ((((mid.x + r) + u.y) + d.y) + below.y) + above.y;
+    double v0, v1;
+    if (FAST_DIV) {
+        v0 = fast_third(s0) - p.x;
+        v1 = fast_third(s1) - p.y;
+    } else {
+        v0 = s0 / 3.0 - p.x;
+        v1 = s1 / 3.0 - p.y;
+    }
+    const unsigned c0 = ck & 0xffu, c1 = ck >> 8;
+    if (c0 != CLS_AIR) v0 = 0.0;
+    if (c1 != CLS_AIR) v1 = 0.0;
+    if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {  // rare: inf / nan
+        if (FAST_DIV) {
+            if (c0 == CLS_AIR) v0 = slow_third(s0) - p.x;
+            if (c1 == CLS_AIR) v1 = slow_third(s1) - p.y;
+        }
+        bad |= classify_bad(v0) | classify_bad(v1);
+    }
+    if (c0 != CLS_BOUNDARY && c1 != CLS_BOUNDARY) {
+        st2(dst, make_double2(v0, v1));
+    } else {
+        if (c0 != CLS_BOUNDARY) dst[0] = v0;
+        if (c1 != CLS_BOUNDARY) dst[1] = v1;
+    }
+}
+
 // ---------------------------------------------------------------------------
-// Variant DIRECT: register z-march, plain coalesced 16-byte loads; x/y
-// neighbours come through L1. Bring-up kernel and cross-check for the TMA one.
+// Variant DIRECT: register z-march; each thread owns one node pair of a row and
+// walks a z-chunk. The three z-planes rotate through registers (unrolled by 3,
+// no moves), x/y neighbours come through L1, and the planes PF iterations ahead
+// are pulled into L2 with prefetch.global.L2.
 // grid = (ceil(dx/2/BX), ceil(dy/BY), zchunks), block = (BX, BY).
 // ---------------------------------------------------------------------------
 template <int BX, int BY, bool FAST_DIV, int PF>
@@ -135,71 +170,55 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
               const uint8_t* __restrict__ code, WgGeom g, int zchunk, int* __restrict__ flag) {
     const int x0 = 2 * (blockIdx.x * BX + threadIdx.x);
     const int y = blockIdx.y * BY + threadIdx.y;
-    const bool active = (x0 < g.dx) && (y < g.dy);
     const int zs = 1 + blockIdx.z * zchunk;
     const int ze = min(zs + zchunk, g.nzl + 1);
     int bad = 0;
-    if (active && zs < ze) {
-        const bool has1 = x0 + 1 < g.dx;
-        const bool hasL = x0 > 0, hasR = x0 + 2 < g.dx;
-        const bool hasU = y > 0, hasD = y + 1 < g.dy;
-        long long off = ((long long)zs * g.dy + y) * g.px + x0;
-        long long coff = ((long long)zs * g.dy + y) * g.pc + x0;
-        double2 below = ld2(cur + off - g.plane);
-        double2 mid = ld2(cur + off);
-        double2 above = ld2(cur + off + g.plane);
-        double2 p = ld2(prev + off);
-        uchar2 c = *reinterpret_cast<const uchar2*>(code + coff);
-        for (int z = zs; z < ze; ++z, off += g.plane, coff += g.cplane) {
-            // the three streaming operands of the NEXT iteration are requested
-            // before this iteration's arithmetic (software pipelining) ...
-            double2 above_n = make_double2(0.0, 0.0), p_n = make_double2(0.0, 0.0);
-            uchar2 c_n = make_uchar2(0, 0);
-            if (z + 1 < ze) {
-                above_n = ld2(cur + off + 2 * g.plane);
-                p_n = ld2(prev + off + g.plane);
-                c_n = *reinterpret_cast<const uchar2*>(code + coff + g.cplane);
-            }
-            // ... and the planes PF iterations ahead are pulled into L2
+    if (x0 < g.dx && y < g.dy && zs < ze) {
+        const uint32_t sp = (uint32_t)g.plane;
+        const uint32_t row = (uint32_t)g.px;
+        const uint32_t ksp = (uint32_t)g.cplane;
+        uint32_t off = (uint32_t)wg_offset(g, x0, y, zs);
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y) * g.pc + x0);
+        int z = zs;
+        auto iter = [&](const double2& below, const double2& mid, double2& above) {
+            above = ld2(cur + (off + sp));
+            const double2 p = ld2(prev + off);
+            const unsigned ck = *reinterpret_cast<const unsigned short*>(code + koff);
             if (PF > 0 && z + PF <= g.nzl) {
-                prefetch_l2(cur + off + (long long)(PF + 1) * g.plane);
-                prefetch_l2(prev + off + (long long)PF * g.plane);
+                prefetch_l2(cur + (off + (PF + 1) * sp));
+                prefetch_l2(prev + (off + PF * sp));
             }
-            const double l = hasL ? cur[off - 1] : 0.0;
-            const double r = hasR ? cur[off + 2] : 0.0;
-            const double2 u = hasU ? ld2(cur + off - g.px) : make_double2(0.0, 0.0);
-            const double2 d = hasD ? ld2(cur + off + g.px) : make_double2(0.0, 0.0);
-            const double right0 = has1 ? mid.y : 0.0;
-            double v0 = air_update<FAST_DIV>(l, right0, u.x, d.x, below.x, above.x, p.x);
-            double v1 = air_update<FAST_DIV>(mid.x, r, u.y, d.y, below.y, above.y, p.y);
-            if (c.x != CLS_AIR) v0 = 0.0;
-            if (c.y != CLS_AIR) v1 = 0.0;
-            const bool w0 = c.x != CLS_BOUNDARY;
-            const bool w1 = has1 && c.y != CLS_BOUNDARY;
-            if (w0) bad |= classify_bad(v0);
-            if (w1) bad |= classify_bad(v1);
-            if (w0 && w1) {
-                st2(prev + off, make_double2(v0, v1));
-            } else {
-                if (w0) prev[off] = v0;
-                if (w1) prev[off + 1] = v1;
-            }
-            below = mid;
-            mid = above;
-            above = above_n;
-            p = p_n;
-            c = c_n;
+            const double l = cur[off - 1];
+            const double r = cur[off + 2];
+            const double2 u = ld2(cur + (off - row));
+            const double2 d = ld2(cur + (off + row));
+            update_pair<FAST_DIV>(l, mid, r, u, d, below, above, p, ck, prev + off, bad);
+            off += sp;
+            koff += ksp;
+            ++z;
+        };
+        double2 a, b = ld2(cur + (off - sp)), c = ld2(cur + off);
+        while (z + 3 <= ze) {
+            iter(b, c, a);
+            iter(c, a, b);
+            iter(a, b, c);
+        }
+        if (z < ze) {
+            iter(b, c, a);
+            if (z < ze) iter(c, a, b);
         }
     }
     raise_flags(bad, flag);
 }
 
-// test hook: out[i] = third<true>(in[i]) and ref[i] = in[i] / 3.0
+// test hook: the kernels' division by 3 (with its inf fix-up) next to `/ 3.0`
 __global__ void wg_third_test(const double* __restrict__ in, double* __restrict__ fast,
                               double* __restrict__ ref, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) {
-        fast[i] = third<true>(in[i]);
+        double v = fast_third(in[i]);
+        if (abs_hi(v) >= 0x7ff00000u) v = slow_third(in[i]);
+        fast[i] = v;
         ref[i] = in[i] / 3.0;
     }
 }
@@ -207,20 +226,20 @@ __global__ void wg_third_test(const double* __restrict__ in, double* __restrict_
 // ---------------------------------------------------------------------------
 // Variant TMA: each CTA owns a TX x TY column of the slab and marches in z.
 // One elected thread streams (TX+4) x (TY+2) x 1 boxes of `cur` into a ring of
-// shared-memory plane buffers with cp.async.bulk.tensor (out-of-mesh parts of
-// a box are zero-filled by the TMA unit = "skip off-mesh ports"); the three
-// live planes z-1, z, z+1 supply all seven stencil points from shared memory,
-// so every `cur` value is fetched from L2/HBM once per CTA (plus halo).
-// `prev` and the class bytes are read with coalesced 16-byte / 2-byte loads
-// one iteration ahead, results stored with 16-byte stores.
+// shared-memory plane buffers with cp.async.bulk.tensor; the three live planes
+// z-1, z, z+1 supply all seven stencil points from shared memory, so every
+// `cur` value is fetched from L2/HBM once per CTA (plus halo) and the stencil
+// reads cost 32-bit shared-memory addresses only. `prev` and the class bytes
+// are read with coalesced 16-byte / 2-byte loads one iteration ahead, results
+// stored with 16-byte stores.
 // ---------------------------------------------------------------------------
 namespace tma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,12 +247,11 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -242,20 +260,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "@p bra DONE_%=;\n"
             "bra WAIT_%=;\n"
             "DONE_%=:\n"
-            "}\n" ::"r"(smem_u32(bar)),
+            "}\n" ::"r"(bar),
             "r"(parity)
             : "memory");
 }
-__device__ __forceinline__ void load_box_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+__device__ __forceinline__ void load_box_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2) {
     asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-            " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-            "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+            " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
             : "memory");
 }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds1(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
 }
 
 }  // namespace tma
@@ -281,15 +309,14 @@ struct TmaCfg {
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-wg_air_tma(const __grid_constant__ CUtensorMap cur_map, const double* __restrict__ /*cur*/,
-           double* __restrict__ prev, const uint8_t* __restrict__ code, WgGeom g, int zchunks,
-           int* __restrict__ flag) {
+wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ prev,
+           const uint8_t* __restrict__ code, WgGeom g, int zchunks, int* __restrict__ flag) {
     constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
+    constexpr int R = Cfg::ROWS_PER_THREAD;
     extern __shared__ unsigned char smem_raw[];
-    // 128-byte aligned stage ring followed by the mbarriers
-    unsigned char* base = reinterpret_cast<unsigned char*>(
-            (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES);
+    // 128-byte aligned stage ring followed by the mbarriers (shared-window addresses)
+    const uint32_t base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t bars = base + NS * Cfg::STAGE_BYTES;
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX;
@@ -297,110 +324,118 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, const double* __restrict
     // z range of this CTA: owned local planes [zs, ze)
     const int zs = 1 + (int)(((long long)g.nzl * blockIdx.z) / zchunks);
     const int ze = 1 + (int)(((long long)g.nzl * (blockIdx.z + 1)) / zchunks);
-    const int first_plane = zs - 1;       // planes first_plane .. ze are streamed
-    const int n_planes = ze - zs + 2;
+    const int n_planes = ze - zs + 2;  // planes zs-1 .. ze are streamed
 
     if (tid == 0) {
         tma::prefetch_map(&cur_map);
-        for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
+        for (int s = 0; s < NS; ++s) tma::mbar_init(bars + 8 * s, 1);
         tma::fence_barrier_init();
         tma::fence_proxy_async();
     }
     __syncthreads();
 
-    auto stage_ptr = [&](int q) -> double* {
-        return reinterpret_cast<double*>(base + (q % NS) * Cfg::STAGE_BYTES);
-    };
-    auto issue = [&](int q) {  // q = plane number relative to first_plane
-        uint64_t* bar = &full[q % NS];
-        tma::mbar_arrive_expect_tx(bar, Cfg::BOX_BYTES);
-        tma::load_box_3d(stage_ptr(q), &cur_map, bar, x0 - Cfg::HX, y0 - 1, first_plane + q);
-    };
+    // box origin in the padded array: column WG_XO + x0 - HX, row (y0 - 1) + 1
+    const int bx = WG_XO + x0 - Cfg::HX, by = y0;
+    int issued = 0;  // planes requested so far (meaningful in thread 0 only)
     if (tid == 0) {
         const int pre = n_planes < NS ? n_planes : NS;
-        for (int q = 0; q < pre; ++q) issue(q);
+        for (; issued < pre; ++issued) {
+            tma::mbar_arrive_expect_tx(bars + 8 * issued, Cfg::BOX_BYTES);
+            tma::load_box_3d(base + issued * Cfg::STAGE_BYTES, &cur_map, bars + 8 * issued, bx, by,
+                             zs - 1 + issued);
+        }
     }
 
     // thread -> nodes: pair column tx (x = x0 + 2 tx), rows ty + 4 rr
     const int tx = tid & 63;
     const int ty = tid >> 6;
     const int x = x0 + 2 * tx;
-    const bool xin = x < g.dx;
-    const bool has1 = x + 1 < g.dx;
-
-    double2 p_next[Cfg::ROWS_PER_THREAD];
-    uchar2 c_next[Cfg::ROWS_PER_THREAD];
-    auto fetch = [&](int z) {
+    bool valid[R];
 #pragma unroll
-        for (int rr = 0; rr < Cfg::ROWS_PER_THREAD; ++rr) {
-            const int y = y0 + ty + 4 * rr;
-            if (xin && y < g.dy) {
-                const long long row = (long long)z * g.dy + y;
-                p_next[rr] = ld2(prev + row * g.px + x);
-                c_next[rr] = *reinterpret_cast<const uchar2*>(code + row * g.pc + x);
-            } else {
-                p_next[rr] = make_double2(0.0, 0.0);
-                c_next[rr] = make_uchar2(CLS_BOUNDARY, CLS_BOUNDARY);
-            }
-        }
-    };
-    fetch(zs);
+    for (int rr = 0; rr < R; ++rr) valid[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
+    const uint32_t sp = (uint32_t)g.plane, ksp = (uint32_t)g.cplane;
+    uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, zs);  // row rr: + 4 rr px
+    uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + x);
+    const uint32_t rstep = 4u * (uint32_t)g.px, krstep = 4u * (uint32_t)g.pc;
+    // byte offset of this thread's centre pair inside a stage (row rr: + 4 rr BOXX 8)
+    const uint32_t so = (uint32_t)(((ty + 1) * BOXX + 2 * tx + Cfg::HX) * 8);
 
-    // planes 0 and 1 of the chunk must have landed before the first iteration
-    tma::mbar_wait(&full[0 % NS], 0);
-    tma::mbar_wait(&full[1 % NS], 0);
+    double2 p_next[R];
+    unsigned c_next[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        p_next[rr] = make_double2(0.0, 0.0);
+        c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 8);
+        if (valid[rr]) {
+            p_next[rr] = ld2(prev + (off + rr * rstep));
+            c_next[rr] = *reinterpret_cast<const unsigned short*>(code + (koff + rr * krstep));
+        }
+    }
+
+    // ring state: stage of plane z-1, stage + phase bit of plane z+1
+    int st_b = 0;
+    int st_a = 2;
+    uint32_t ph_a = 0;
+    tma::mbar_wait(bars + 0, 0);
+    tma::mbar_wait(bars + 8, 0);
 
     int bad = 0;
     for (int z = zs; z < ze; ++z) {
-        const int q = z - first_plane;  // plane z; q-1 below, q+1 above
-        tma::mbar_wait(&full[(q + 1) % NS], ((q + 1) / NS) & 1);
-        const double* sm = stage_ptr(q);
-        const double* sb = stage_ptr(q - 1);
-        const double* sa = stage_ptr(q + 1);
+        tma::mbar_wait(bars + 8 * st_a, ph_a);
+        int st_m = st_b + 1;
+        if (st_m == NS) st_m = 0;
+        const uint32_t sb = base + st_b * Cfg::STAGE_BYTES + so;
+        const uint32_t sm = base + st_m * Cfg::STAGE_BYTES + so;
+        const uint32_t sa = base + st_a * Cfg::STAGE_BYTES + so;
 
-        double2 p[Cfg::ROWS_PER_THREAD];
-        uchar2 c[Cfg::ROWS_PER_THREAD];
+        double2 p[R];
+        unsigned c[R];
 #pragma unroll
-        for (int rr = 0; rr < Cfg::ROWS_PER_THREAD; ++rr) {
+        for (int rr = 0; rr < R; ++rr) {
             p[rr] = p_next[rr];
             c[rr] = c_next[rr];
         }
-        if (z + 1 < ze) fetch(z + 1);
-
+        if (z + 1 < ze) {
 #pragma unroll
-        for (int rr = 0; rr < Cfg::ROWS_PER_THREAD; ++rr) {
-            const int r = ty + 4 * rr;
-            const int y = y0 + r;
-            const int o = (r + 1) * BOXX + 2 * tx + Cfg::HX;
-            const double2 mid = ld2(sm + o);
-            const double l = sm[o - 1];
-            const double rgt = sm[o + 2];
-            const double2 u = ld2(sm + o - BOXX);
-            const double2 d = ld2(sm + o + BOXX);
-            const double2 below = ld2(sb + o);
-            const double2 above = ld2(sa + o);
-            double v0 = air_update<Cfg::FAST_DIV>(l, mid.y, u.x, d.x, below.x, above.x, p[rr].x);
-            double v1 = air_update<Cfg::FAST_DIV>(mid.x, rgt, u.y, d.y, below.y, above.y, p[rr].y);
-            if (c[rr].x != CLS_AIR) v0 = 0.0;
-            if (c[rr].y != CLS_AIR) v1 = 0.0;
-            const bool inb = xin && y < g.dy;
-            const bool w0 = inb && c[rr].x != CLS_BOUNDARY;
-            const bool w1 = inb && has1 && c[rr].y != CLS_BOUNDARY;
-            if (w0) bad |= classify_bad(v0);
-            if (w1) bad |= classify_bad(v1);
-            double* dst = prev + ((long long)z * g.dy + y) * g.px + x;
-            if (w0 && w1) {
-                st2(dst, make_double2(v0, v1));
-            } else {
-                if (w0) dst[0] = v0;
-                if (w1) dst[1] = v1;
+            for (int rr = 0; rr < R; ++rr) {
+                if (valid[rr]) {
+                    p_next[rr] = ld2(prev + (off + sp + rr * rstep));
+                    c_next[rr] =
+                            *reinterpret_cast<const unsigned short*>(code + (koff + ksp + rr * krstep));
+                }
             }
         }
-        // everyone is done with plane q-1: its buffer may be refilled
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            if (valid[rr]) {
+                const uint32_t o = rr * (4 * BOXX * 8);
+                const double2 mid = tma::lds2(sm + o);
+                const double l = tma::lds1(sm + o - 8);
+                const double rgt = tma::lds1(sm + o + 16);
+                const double2 u = tma::lds2(sm + o - BOXX * 8);
+                const double2 d = tma::lds2(sm + o + BOXX * 8);
+                const double2 below = tma::lds2(sb + o);
+                const double2 above = tma::lds2(sa + o);
+                update_pair<Cfg::FAST_DIV>(l, mid, rgt, u, d, below, above, p[rr], c[rr],
+                                           prev + (off + rr * rstep), bad);
+            }
+        }
+        off += sp;
+        koff += ksp;
+        // everyone is done with plane z-1: its buffer may be refilled
         __syncthreads();
-        if (tid == 0) {
-            const int qn = q - 1 + NS;
-            if (qn < n_planes) issue(qn);
+        if (tid == 0 && issued < n_planes) {
+            // the freed stage gets the next plane; its barrier moves on to the next phase
+            tma::mbar_arrive_expect_tx(bars + 8 * st_b, Cfg::BOX_BYTES);
+            tma::load_box_3d(base + st_b * Cfg::STAGE_BYTES, &cur_map, bars + 8 * st_b, bx, by,
+                             zs - 1 + issued);
+            ++issued;
+        }
+        st_b = st_m;
+        ++st_a;
+        if (st_a == NS) {
+            st_a = 0;
+            ph_a ^= 1u;
         }
     }
     raise_flags(bad, flag);
@@ -555,7 +590,7 @@ __global__ void flag_expand(const int* __restrict__ flag, int* __restrict__ out5
     const int i = threadIdx.x;
     if (i < 5) out5[i] = (*flag >> i) & 1;
 }
-// owned planes of `cur` -> dense float (the GUI's pressure view)
+// owned planes of `cur` -> dense float array (x fastest, no padding)
 __global__ void wg_to_f32(const double* __restrict__ cur, float* __restrict__ out, WgGeom g) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n = (long long)g.dx * g.dy * g.nzl;
@@ -564,7 +599,7 @@ __global__ void wg_to_f32(const double* __restrict__ cur, float* __restrict__ ou
         const long long r = i / g.dx;
         const int y = r % g.dy;
         const long long z = r / g.dy;
-        out[i] = (float)cur[((z + 1) * g.dy + y) * g.px + x];
+        out[i] = (float)cur[wg_offset(g, x, y, z + 1)];
     }
 }
 
