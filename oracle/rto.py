@@ -1,0 +1,142 @@
+"""ctypes front-end of the CPU ray-tracing oracle (oracle/rt_oracle.cpp).
+TEST INFRASTRUCTURE ONLY (see wg_oracle.cpp's header)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "librtoracle.so")
+
+REFL_DT = np.dtype([("position", "<f4", (4,)), ("triangle", "<u4"), ("keep_going", "i1"),
+                    ("receiver_visible", "i1"), ("pad", "i1", (10,))])
+
+
+class TraceParams(C.Structure):
+    _fields_ = [
+        ("source", C.c_float * 3), ("receiver", C.c_float * 3),
+        ("receiver_radius", C.c_float), ("pad0", C.c_float),
+        ("speed_of_sound", C.c_double), ("histogram_rate", C.c_double),
+        ("total_rays", C.c_uint64), ("seed", C.c_uint64), ("ray_index_base", C.c_uint64),
+        ("depth", C.c_uint32), ("specular_from_step", C.c_uint32), ("n_bins", C.c_uint32),
+        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("pad1", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "rt_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "_build/librtoracle.so"], check=True, stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.rto_scene_create.restype = vp
+        L.rto_scene_create.argtypes = [vp, sz, vp, C.c_uint32, vp, sz, vp, sz, vp, sz]
+        L.rto_scene_destroy.argtypes = [vp]
+        L.rto_closest_hit.argtypes = [vp, vp, sz, C.c_int, vp, vp]
+        L.rto_ray_energy.restype = C.c_float
+        L.rto_ray_energy.argtypes = [C.c_uint64, vp, vp, C.c_float]
+        L.rto_directions.argtypes = [C.c_uint64, C.c_uint64, sz, vp]
+        L.rto_sincos.argtypes = [vp, sz, vp, vp]
+        L.rto_lut_index.argtypes = [vp, sz, vp, vp]
+        L.rto_trace.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+        L.rto_num_threads.restype = C.c_int
+        L.rto_params_size.restype = sz
+        assert L.rto_params_size() == C.sizeof(TraceParams)
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    def __init__(self, sc):
+        """sc: a wayverb_b200.scene.Scene (or anything with the same arrays)."""
+        self.sc = sc
+        self._h = lib().rto_scene_create(_p(sc.voxel_index), sc.voxel_index.size, _p(sc.aabb), sc.side,
+                                         _p(sc.triangles), sc.triangles.size, _p(sc.vertices),
+                                         sc.vertices.shape[0], _p(sc.surfaces), sc.surfaces.size)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().rto_scene_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def closest_hit(self, pos, dirs, brute=False):
+        rays = np.ascontiguousarray(np.concatenate([pos, dirs], 1), np.float32)
+        n = rays.shape[0]
+        tri = np.zeros(n, np.uint32)
+        t = np.zeros(n, np.float32)
+        lib().rto_closest_hit(self._h, _p(rays), n, int(brute), _p(tri), _p(t))
+        return tri, t
+
+    def trace(self, dirs, source, receiver, depth, total_rays=None, receiver_radius=0.1, speed_of_sound=340.0,
+              histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0, n_bins=None,
+              directional=False, keep_steps=0):
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        P = TraceParams()
+        P.source[:] = [float(v) for v in source]
+        P.receiver[:] = [float(v) for v in receiver]
+        P.receiver_radius = receiver_radius
+        P.speed_of_sound, P.histogram_rate = speed_of_sound, histogram_rate
+        P.total_rays = n if total_rays is None else total_rays
+        P.seed, P.ray_index_base = seed, ray_index_base
+        P.depth, P.specular_from_step = depth, specular_from_step
+        if n_bins is None:
+            n_bins = int(np.ceil((depth + 1) * self.sc.diagonal / speed_of_sound * histogram_rate)) + 1
+        P.n_bins, P.directional, P.keep_steps = n_bins, int(directional), keep_steps
+        shape = (20, 9, n_bins, 8) if directional else (n_bins, 8)
+        hist = np.zeros(shape)
+        dropped = C.c_uint64(0)
+        refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
+        lib().rto_trace(self._h, C.byref(P), _p(d), n, _p(hist), C.byref(dropped),
+                        _p(refl) if refl is not None else None)
+        return hist, refl, dropped.value
+
+
+def ray_energy(total_rays, source, receiver, radius):
+    s = np.asarray(source, np.float32)
+    r = np.asarray(receiver, np.float32)
+    return lib().rto_ray_energy(int(total_rays), _p(s), _p(r), float(radius))
+
+
+def directions(seed, n, base=0):
+    out = np.zeros((n, 3), np.float32)
+    lib().rto_directions(int(seed), int(base), n, _p(out))
+    return out
+
+
+def sincos(theta):
+    t = np.ascontiguousarray(theta, np.float32)
+    s, c = np.zeros_like(t), np.zeros_like(t)
+    lib().rto_sincos(_p(t), t.size, _p(s), _p(c))
+    return s, c
+
+
+def lut_index(v):
+    v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)
+    az, el = np.zeros(v.shape[0], np.int32), np.zeros(v.shape[0], np.int32)
+    lib().rto_lut_index(_p(v), v.shape[0], _p(az), _p(el))
+    return az, el
+
+
+def num_threads():
+    return lib().rto_num_threads()

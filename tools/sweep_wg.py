@@ -27,15 +27,15 @@ def main():
     m = wvb.cuboid_mesh(dims, [plaster()])
     nodes = dims[0] * dims[1] * dims[2]
     configs = []
-    for div, pf, zc in itertools.product((1, 0), (4, 0, 8), (16, 8, 32)):
-        if div == 0 and pf == 8:
-            continue
-        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=div, WVB_WG_PF=pf, WVB_WG_ZCHUNKS=zc))
-    for st, mb, zc in itertools.product((5, 4), (1, 4), (12, 16, 24)):
+    for ov in (1, 0):
+        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
+                            WVB_WG_DIV=1, WVB_WG_OVERLAP=ov))
+        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=1, WVB_WG_PF=4, WVB_WG_ZCHUNKS=32, WVB_WG_OVERLAP=ov))
+    for st, mb, zc in ((4, 1, 12), (5, 1, 24), (5, 1, 37), (6, 1, 12), (5, 4, 24)):
         configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=st, WVB_WG_MINB=mb, WVB_WG_ZCHUNKS=zc,
-                            WVB_WG_DIV=1))
-    configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
-                        WVB_WG_DIV=0))
+                            WVB_WG_DIV=1, WVB_WG_OVERLAP=1))
+    for pf, zc in ((4, 64), (2, 32), (6, 32)):
+        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=1, WVB_WG_PF=pf, WVB_WG_ZCHUNKS=zc, WVB_WG_OVERLAP=1))
     only = os.environ.get("SWEEP_ONLY")
     for cfg in configs:
         if only and cfg["WVB_WG_KERNEL"] != only:

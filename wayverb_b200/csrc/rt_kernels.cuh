@@ -1,0 +1,437 @@
+// rt_kernels.cuh -- sm_100a device code of the stochastic ray-reflection loop.
+//
+// The reference drives, per reflection step and per 16384-ray segment, one
+// `reflections` launch (src/raytracer/src/program.cpp:59-153), one `stochastic`
+// launch (src/raytracer/src/stochastic/program.cpp:58-152), three bulk H2D and
+// three bulk D2H copies, host RNG and a host histogram loop
+// (raytracer.h:223-244, reflector.cpp:31-51, stochastic/finder.h:48-79,
+// reflection_processor/stochastic_histogram.h:70-111). Here one thread owns one
+// ray for its whole life: closest hit by voxel DDA, receiver visibility, next
+// direction, energy bookkeeping and histogram binning all happen in registers,
+// and only the histogram (fp64 atomics) and the optional first-steps
+// reflection records touch memory.
+//
+// fp32 arithmetic in the reference's operation order (-fmad=false). Random
+// numbers and sin/cos are the fixed definitions shared with the oracle (see
+// oracle/rt_oracle.cpp's header): Philox4x32-10 keyed by (seed), counter =
+// (global ray index, step, stream); Cody-Waite + polynomial sincos.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace wvb {
+namespace rt {
+
+struct f3 {
+    float x, y, z;
+};
+
+// reference PODs as they arrive (scene_buffers.h:14-38)
+struct alignas(16) TriPod {  // core::triangle
+    uint32_t surface, v0, v1, v2;
+};
+struct alignas(16) ReflectionPod {  // raytracer::reflection, 32 B  (raytracer/cl/reflection.h:10-17)
+    float px, py, pz, pw;
+    uint32_t triangle;
+    int8_t keep_going;
+    int8_t receiver_visible;
+    int8_t pad_[10];
+};
+static_assert(sizeof(ReflectionPod) == 32, "reflection layout");
+
+// per-triangle data derived once at create time with the same fp32 operations
+// the per-ray code would use: v0, e0 = v1 - v0, e1 = v2 - v0 and the unit
+// normal (triangle_verts_normal, geometry.cpp:69-74).
+struct alignas(16) TriPre {
+    float v0x, v0y, v0z, nx;
+    float e0x, e0y, e0z, ny;
+    float e1x, e1y, e1z, nz;
+};
+
+struct Scene {
+    const uint32_t* voxel_index;
+    const TriPod* triangles;
+    const TriPre* pre;
+    const float* surfaces;  // 16 floats per surface: absorption[8], scattering[8]
+    f3 c0, c1;
+    uint32_t side;
+    uint32_t n_triangles;
+};
+
+struct Params {
+    f3 source, receiver;
+    float receiver_radius;
+    float ray_energy;
+    double speed_of_sound;
+    double histogram_rate;
+    unsigned long long seed;
+    unsigned long long ray_index_base;
+    uint32_t depth;
+    uint32_t specular_from_step;
+    uint32_t n_bins;
+    uint32_t directional;
+    uint32_t keep_steps;
+};
+
+__device__ __forceinline__ f3 mk(float x, float y, float z) { return {x, y, z}; }
+__device__ __forceinline__ f3 add(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 sub(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 mul(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float length(f3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ f3 normalize(f3 a) { return mul(a, 1.0f / sqrtf(dot(a, a))); }
+
+// ---- Philox4x32-10 ---------------------------------------------------------------
+__device__ __forceinline__ void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                       uint32_t k0, uint32_t k1, uint32_t& o0, uint32_t& o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o0 = c0;
+    o1 = c1;
+}
+__device__ __forceinline__ void direction_rng(unsigned long long seed, uint32_t ray, uint32_t step,
+                                              uint32_t stream, float& z, float& theta) {
+    uint32_t o0, o1;
+    philox(ray, step, stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1);
+    const float u0 = (float)(o0 >> 8) * 5.9604644775390625e-08f;
+    const float u1 = (float)(o1 >> 8) * 5.9604644775390625e-08f;
+    z = 2.0f * u0 - 1.0f;
+    theta = (2.0f * u1 - 1.0f) * 3.14159274101257324f;
+}
+
+__device__ __forceinline__ void sincos_fixed(float theta, float& s, float& c) {
+    const float kf = rintf(theta * 0.636619746685028076f);
+    const int k = (int)kf;
+    float r = theta - kf * 1.57079625129699707f;
+    r = r - kf * 7.54978941586159635e-08f;
+    const float r2 = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = ps * r2 + 8.3321608736e-3f;
+    ps = ps * r2 + -1.6666654611e-1f;
+    const float sin_r = r + (r * r2) * ps;
+    float pc = 2.443315711809948e-5f;
+    pc = pc * r2 + -1.388731625493765e-3f;
+    pc = pc * r2 + 4.166664568298827e-2f;
+    const float cos_r = (1.0f - 0.5f * r2) + (r2 * r2) * pc;
+    switch (k & 3) {
+        case 0: s = sin_r; c = cos_r; break;
+        case 1: s = cos_r; c = -sin_r; break;
+        case 2: s = -sin_r; c = -cos_r; break;
+        default: s = -cos_r; c = sin_r; break;
+    }
+}
+
+// sphere_point                  brdf.cpp:7-11
+__device__ __forceinline__ f3 sphere_point(float z, float theta) {
+    const float t = sqrtf(1 - z * z);
+    float s, c;
+    sincos_fixed(theta, s, c);
+    return {t * c, z, t * s};
+}
+
+// almost_equal                  geometry.cpp:7-11
+__device__ __forceinline__ bool almost_equal(float x, float y, float ulp) {
+    const float abs_diff = fabsf(x - y);
+    return abs_diff < FLT_EPSILON * fabsf(x + y) * ulp || abs_diff < FLT_MIN;
+}
+
+// triangle_vert_intersection    geometry.cpp:20-54   (returns t, 0 = no hit)
+__device__ __forceinline__ float tri_intersection(const TriPre& T, f3 pos, f3 dir) {
+    const f3 e0 = mk(T.e0x, T.e0y, T.e0z);
+    const f3 e1 = mk(T.e1x, T.e1y, T.e1z);
+    const f3 pvec = cross(dir, e1);
+    const float det = dot(e0, pvec);
+    if (almost_equal(det, 0, 10.0f)) return 0.0f;
+    const float invdet = 1.0f / det;
+    const f3 tvec = sub(pos, mk(T.v0x, T.v0y, T.v0z));
+    const float u = invdet * dot(tvec, pvec);
+    if (u < 0.0f || 1.0f < u) return 0.0f;
+    const f3 qvec = cross(tvec, e0);
+    const float v = invdet * dot(dir, qvec);
+    if (v < 0.0f || 1.0f < v + u) return 0.0f;
+    const float t = invdet * dot(e1, qvec);
+    if (t < 0 || almost_equal(t, 0, 10.0f)) return 0.0f;
+    return t;
+}
+
+// VOXEL_TRAVERSAL_ALGORITHM + voxel_traversal + ray_triangle_group_intersection
+// (voxel.cpp:22-95, geometry.cpp:103-148). Returns t (0 = none) and the index.
+__device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir, uint32_t avoid,
+                                                 uint32_t& index) {
+    index = 0;
+    const float sidef = (float)sc.side;
+    const f3 vd = mk((sc.c1.x - sc.c0.x) / sidef, (sc.c1.y - sc.c0.y) / sidef,
+                     (sc.c1.z - sc.c0.z) / sidef);
+    const f3 rel = mk((pos.x - sc.c0.x) / vd.x, (pos.y - sc.c0.y) / vd.y, (pos.z - sc.c0.z) / vd.z);
+    int ix = (int)floorf(rel.x), iy = (int)floorf(rel.y), iz = (int)floorf(rel.z);
+    const int side = (int)sc.side;
+    if (!(0 <= ix && 0 <= iy && 0 <= iz && ix < side && iy < side && iz < side)) return 0.0f;
+    const f3 lo = mk(sc.c0.x + (float)ix * vd.x, sc.c0.y + (float)iy * vd.y, sc.c0.z + (float)iz * vd.z);
+    const f3 hi = mk(sc.c0.x + (float)(ix + 1) * vd.x, sc.c0.y + (float)(iy + 1) * vd.y,
+                     sc.c0.z + (float)(iz + 1) * vd.z);
+    const bool ngx = signbit(dir.x), ngy = signbit(dir.y), ngz = signbit(dir.z);
+    const int stx = ngx ? -1 : 1, sty = ngy ? -1 : 1, stz = ngz ? -1 : 1;
+    const int jox = ngx ? -1 : side, joy = ngy ? -1 : side, joz = ngz ? -1 : side;
+    float tmx = fabsf(((ngx ? lo.x : hi.x) - pos.x) / dir.x);
+    float tmy = fabsf(((ngy ? lo.y : hi.y) - pos.y) / dir.y);
+    float tmz = fabsf(((ngz ? lo.z : hi.z) - pos.z) / dir.z);
+    if (isnan(tmx)) tmx = INFINITY;
+    if (isnan(tmy)) tmy = INFINITY;
+    if (isnan(tmz)) tmz = INFINITY;
+    const float tdx = fabsf(vd.x / dir.x), tdy = fabsf(vd.y / dir.y), tdz = fabsf(vd.z / dir.z);
+    for (;;) {
+        int min_i = 0;
+        float tmin = tmx;
+        if (tmy < tmin) { min_i = 1; tmin = tmy; }
+        if (tmz < tmin) { min_i = 2; tmin = tmz; }
+        const uint32_t voxel_offset =
+                sc.voxel_index[(size_t)ix * side * side + (size_t)iy * side + iz];
+        const uint32_t num = sc.voxel_index[voxel_offset];
+        const uint32_t* begin = sc.voxel_index + voxel_offset + 1;
+        float best_t = 0.0f;
+        uint32_t best_i = 0;
+        for (uint32_t i = 0; i != num; ++i) {
+            const uint32_t ti = begin[i];
+            if (ti != avoid) {
+                const float t = tri_intersection(sc.pre[ti], pos, dir);
+                if (t && (!best_t || t < best_t)) {
+                    best_i = ti;
+                    best_t = t;
+                }
+            }
+        }
+        if (best_t && best_t <= tmin) {
+            index = best_i;
+            return best_t;
+        }
+        if (min_i == 0) {
+            ix += stx;
+            if (ix == jox) break;
+            tmx += tdx;
+        } else if (min_i == 1) {
+            iy += sty;
+            if (iy == joy) break;
+            tmy += tdy;
+        } else {
+            iz += stz;
+            if (iz == joz) break;
+            tmz += tdz;
+        }
+    }
+    return 0.0f;
+}
+
+// voxel_point_intersection      voxel.cpp:227-258
+__device__ __forceinline__ bool point_visible(const Scene& sc, f3 begin, f3 point, uint32_t avoid) {
+    const f3 b2p = sub(point, begin);
+    const float mag = length(b2p);
+    const f3 direction = normalize(b2p);
+    uint32_t idx;
+    const float t = voxel_traversal(sc, begin, direction, avoid, idx);
+    return !t || mag < t;
+}
+
+// line_segment_sphere_intersection   geometry.cpp:155-164
+__device__ __forceinline__ bool segment_sphere(f3 p1, f3 p2, f3 c, float r) {
+    const f3 diff = sub(p2, p1);
+    const float u = dot(sub(c, p1), diff) / dot(diff, diff);
+    if (u < 0 || 1 < u) return false;
+    const f3 closest = sub(add(p1, mul(diff, u)), c);
+    return dot(closest, closest) < r * r;
+}
+
+__device__ __forceinline__ float signbit_scalar(float x) { return signbit(x) ? 1.0f : 0.0f; }
+
+// vector_look_up_table<..,20,9>::index (vector_look_up_table.h:53-116, az_el.cpp:53-68)
+__device__ __forceinline__ void lut_index(f3 v, int& az_cell, int& el_cell) {
+    float az = atan2f(v.x, -v.z);
+    const float el = asinf(v.y);
+    if (almost_equal(el, -1.57079637050628662f, 10.0f) || almost_equal(el, 1.57079637050628662f, 10.0f))
+        az = 0;
+    const double deg = 180.0 / 3.14159265358979323846;
+    double a = (double)(-az) * deg;
+    a += (360.0 / 20) / 2;
+    while (a < 0) a += 360;
+    az_cell = (int)((unsigned long long)(a / (360.0 / 20)) % 20ull);
+    double e = (double)el * deg;
+    e += 90 + (180.0 / 10) / 2;
+    while (e < 0) e += 360;
+    unsigned long long adj = (unsigned long long)(e / (180.0 / 10)) % 20ull;
+    if (adj < 1) adj = 1;
+    if (adj > 9) adj = 9;
+    el_cell = (int)(adj - 1);
+}
+
+// one impulse into the histogram (finder.h:65-76 drops distance == 0;
+// energy_histogram_sum, stochastic_histogram.h:17-32)
+__device__ __forceinline__ void deposit(const Params& P, double* __restrict__ hist,
+                                        unsigned long long* __restrict__ dropped,
+                                        const float (&vol)[8], f3 position, float distance) {
+    if (!distance) return;
+    const double time = (double)distance / P.speed_of_sound;
+    const size_t bin = (size_t)(time * P.histogram_rate);
+    if (bin >= P.n_bins) {
+        atomicAdd(dropped, 1ull);
+        return;
+    }
+    size_t base = bin * 8;
+    if (P.directional) {
+        int az, el;
+        lut_index(normalize(sub(position, P.receiver)), az, el);
+        base = (((size_t)az * 9 + el) * P.n_bins + bin) * 8;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) atomicAdd(hist + base + b, (double)vol[b]);
+}
+
+// per-triangle precompute (same ops as triangle_normal / triangle_vert_intersection)
+__global__ void rt_precompute(const TriPod* __restrict__ tris, const float4* __restrict__ verts,
+                              TriPre* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const TriPod t = tris[i];
+        const float4 a = verts[t.v0], b = verts[t.v1], c = verts[t.v2];
+        const f3 v0 = mk(a.x, a.y, a.z);
+        const f3 e0 = sub(mk(b.x, b.y, b.z), v0);
+        const f3 e1 = sub(mk(c.x, c.y, c.z), v0);
+        const f3 nrm = normalize(cross(e0, e1));
+        out[i] = TriPre{v0.x, v0.y, v0.z, nrm.x, e0.x, e0.y, e0.z, nrm.y, e1.x, e1.y, e1.z, nrm.z};
+    }
+}
+
+// directions from Philox stream 1 (random_unit_vector, core/azimuth_elevation.h:31-35)
+__global__ void rt_directions(unsigned long long seed, unsigned long long base, uint32_t n,
+                              float* __restrict__ out3) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float z, th;
+        direction_rng(seed, (uint32_t)(base + i), 0u, 1u, z, th);
+        const f3 d = sphere_point(z, th);
+        out3[3 * (size_t)i] = d.x;
+        out3[3 * (size_t)i + 1] = d.y;
+        out3[3 * (size_t)i + 2] = d.z;
+    }
+}
+
+// closest hit of n rays (test hook mirroring reflector_tests.cpp's comparison)
+__global__ void rt_closest_hit(Scene sc, const float* __restrict__ rays6, uint32_t n,
+                               uint32_t* __restrict__ tri_out, float* __restrict__ t_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const f3 p = mk(rays6[6 * (size_t)i], rays6[6 * (size_t)i + 1], rays6[6 * (size_t)i + 2]);
+        const f3 d = mk(rays6[6 * (size_t)i + 3], rays6[6 * (size_t)i + 4], rays6[6 * (size_t)i + 5]);
+        uint32_t idx;
+        const float t = voxel_traversal(sc, p, d, ~0u, idx);
+        tri_out[i] = t ? idx : ~0u;
+        t_out[i] = t;
+    }
+}
+
+// the whole life of one ray: raytracer.h:223-244 with reflections (program.cpp:59-153),
+// stochastic (stochastic/program.cpp:58-152) and the histogram processor folded in
+__global__ void __launch_bounds__(128)
+rt_trace(Scene sc, Params P, const float* __restrict__ dirs3, uint32_t n, double* __restrict__ hist,
+         unsigned long long* __restrict__ dropped, ReflectionPod* __restrict__ refl_out) {
+    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= n) return;
+    f3 rpos = P.source;
+    f3 rdir = mk(dirs3[3 * (size_t)ri], dirs3[3 * (size_t)ri + 1], dirs3[3 * (size_t)ri + 2]);
+    bool keep_going = true;
+    uint32_t prev_tri = ~0u;
+    float volume[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) volume[b] = P.ray_energy;
+    f3 path_pos = P.source;
+    float path_dist = 0;
+
+    for (uint32_t step = 0; step < P.depth; ++step) {
+        ReflectionPod refl = {};
+        f3 hit = mk(0, 0, 0);
+        uint32_t hit_tri = 0;
+        bool visible = false, alive = false;
+        f3 tnorm_raw = mk(0, 0, 0);
+        if (keep_going) {
+            uint32_t idx;
+            const float t = voxel_traversal(sc, rpos, rdir, prev_tri, idx);
+            if (t) {
+                alive = true;
+                hit = add(rpos, mul(rdir, t));
+                hit_tri = idx;
+                const TriPre T = sc.pre[idx];
+                tnorm_raw = mk(T.nx, T.ny, T.nz);
+                // reflect (geometry.cpp:83-86)
+                const f3 specular = sub(rdir, mul(mul(tnorm_raw, 2), dot(rdir, tnorm_raw)));
+                const f3 tnorm = mul(tnorm_raw, signbit_scalar(dot(tnorm_raw, specular)));
+                visible = point_visible(sc, hit, P.receiver, idx);
+                float z, theta;
+                direction_rng(P.seed, (uint32_t)(P.ray_index_base + ri), step, 0u, z, theta);
+                const f3 rnd = sphere_point(z, theta);
+                const float* sv = sc.surfaces + 16 * (size_t)sc.triangles[idx].surface + 8;
+                const float scatter =
+                        (sv[0] + sv[1] + sv[2] + sv[3] + sv[4] + sv[5] + sv[6] + sv[7]) / 8;
+                const f3 l = mul(rnd, signbit_scalar(dot(rnd, tnorm)));
+                const f3 next = normalize(add(mul(l, scatter), mul(specular, 1 - scatter)));
+                refl.px = hit.x; refl.py = hit.y; refl.pz = hit.z;
+                refl.triangle = idx;
+                refl.keep_going = 1;
+                refl.receiver_visible = visible ? 1 : 0;
+                rpos = hit;
+                rdir = next;
+            }
+        }
+        keep_going = alive;
+        prev_tri = refl.triangle;
+        if (refl_out && step < P.keep_steps) refl_out[(size_t)step * n + ri] = refl;
+        if (!alive) continue;
+
+        const float* sf = sc.surfaces + 16 * (size_t)sc.triangles[hit_tri].surface;
+        float outgoing[8], last_volume[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            last_volume[b] = volume[b];
+            outgoing[b] = volume[b] * (1 - sf[b]);
+            volume[b] = outgoing[b];
+        }
+        const f3 last_position = path_pos;
+        const float last_distance = path_dist;
+        const float this_distance = last_distance + length(sub(last_position, hit));
+        path_pos = hit;
+        path_dist = this_distance;
+
+        if (segment_sphere(last_position, hit, P.receiver, P.receiver_radius)) {
+            const float total = last_distance + length(sub(P.receiver, last_position));
+            if (step >= P.specular_from_step) deposit(P, hist, dropped, last_volume, last_position, total);
+        }
+        if (visible) {
+            const f3 to_receiver = sub(P.receiver, hit);
+            const float trd = length(to_receiver);
+            const float total = this_distance + trd;
+            const float cos_angle = fabsf(dot(tnorm_raw, normalize(to_receiver)));
+            const float sin_y = P.receiver_radius / fmaxf(P.receiver_radius, trd);
+            const float angle_correction = 1 - sqrtf(1 - sin_y * sin_y);
+            float out[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                out[b] = ((angle_correction * 2) * cos_angle) * (outgoing[b] * sf[8 + b]);
+            }
+            deposit(P, hist, dropped, out, hit, total);
+        }
+    }
+}
+
+}  // namespace rt
+}  // namespace wvb

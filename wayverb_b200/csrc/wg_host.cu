@@ -91,7 +91,9 @@ struct wvb_wg {
     dev_buf<int> flag5;
     int* h_flag = nullptr;  // pinned, 8 ints
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream_b = nullptr;  // boundary kernel runs here, next to the air kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
     int ty = 8, nstage = 5, zchunks = 1;
@@ -108,6 +110,9 @@ struct wvb_wg {
         if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (stream_b) cudaStreamDestroy(stream_b);
         if (stream) cudaStreamDestroy(stream);
         if (h_flag) cudaFreeHost(h_flag);
     }
@@ -305,13 +310,18 @@ void launch_air(wvb_wg* w, const double* cur, double* prev) {
     w->launches++;
 }
 
-template <int N>
-void launch_boundary(wvb_wg* w, const double* cur, double* prev) {
-    auto& l = w->bl[N - 1];
-    if (!l.n) return;
-    BList L{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
-    wg_boundary<N><<<(l.n + 127) / 128, 128, 0, w->stream>>>(cur, prev, L, w->coeffs.p, w->g,
-                                                              w->courant, w->courant_sq, w->flag.p);
+void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
+    const uint32_t n1 = w->bl[0].n, n2 = w->bl[1].n, n3 = w->bl[2].n;
+    if (!(n1 + n2 + n3)) return;
+    const uint32_t T = WG_BND_THREADS;
+    const uint32_t nb1 = (n1 + T - 1) / T, nb2 = (n2 + T - 1) / T, nb3 = (n3 + T - 1) / T;
+    auto L = [&](int k) {
+        auto& l = w->bl[k];
+        return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
+    };
+    wg_boundary_all<<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
+                                                      w->coeffs.p, w->g, w->courant, w->courant_sq,
+                                                      w->flag.p);
     w->launches++;
 }
 
@@ -347,10 +357,20 @@ void exchange_ghosts(wvb_wg* w, double* a) {
 void enqueue_launch(wvb_wg* w) {
     const double* cur = w->P[w->cur].p;
     double* prev = w->P[w->cur ^ 1].p;
-    launch_air(w, cur, prev);
-    launch_boundary<1>(w, cur, prev);
-    launch_boundary<2>(w, cur, prev);
-    launch_boundary<3>(w, cur, prev);
+    const bool has_boundary = w->bl[0].n + w->bl[1].n + w->bl[2].n;
+    if (w->overlap && has_boundary) {
+        // the boundary lists and the air kernel write disjoint nodes of `prev`:
+        // fork the boundary launch onto its own (higher priority) stream
+        WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
+        WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
+        launch_boundary(w, cur, prev, w->stream_b);
+        WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
+        launch_air(w, cur, prev);
+        WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+    } else {
+        launch_air(w, cur, prev);
+        launch_boundary(w, cur, prev, w->stream);
+    }
     exchange_ghosts(w, prev);
 }
 // launch + swap (waveguide.h:123)
@@ -518,9 +538,15 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     }
 
     // ---- device state ------------------------------------------------------------
-    WVB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    WVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, prio_lo));
+    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_b, cudaStreamNonBlocking, prio_hi));
     WVB_CUDA(cudaEventCreate(&w->ev0));
     WVB_CUDA(cudaEventCreate(&w->ev1));
+    WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
+    WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
+    w->overlap = env_int("WVB_WG_OVERLAP", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);
@@ -797,11 +823,7 @@ wvb_status wvb_wg_time_kernels(wvb_wg* w, uint32_t n, float ms[2]) {
         WVB_CUDA(cudaEventSynchronize(w->ev1));
         WVB_CUDA(cudaEventElapsedTime(&ms[0], w->ev0, w->ev1));
         WVB_CUDA(cudaEventRecord(w->ev0, w->stream));
-        for (uint32_t i = 0; i < n; ++i) {
-            launch_boundary<1>(w, cur, prev);
-            launch_boundary<2>(w, cur, prev);
-            launch_boundary<3>(w, cur, prev);
-        }
+        for (uint32_t i = 0; i < n; ++i) launch_boundary(w, cur, prev, w->stream);
         WVB_CUDA(cudaEventRecord(w->ev1, w->stream));
         WVB_CUDA(cudaEventSynchronize(w->ev1));
         WVB_CUDA(cudaEventElapsedTime(&ms[1], w->ev0, w->ev1));

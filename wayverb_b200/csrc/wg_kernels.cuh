@@ -474,13 +474,12 @@ __device__ __forceinline__ void filter_step_6(double input, double (&m)[6],
 }
 
 template <int N>
-__global__ void __launch_bounds__(128)
-wg_boundary(const double* __restrict__ cur, double* __restrict__ prev, BList L,
-            const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g, double courant,
-            double courant_sq, int* __restrict__ flag) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ int boundary_node(const double* __restrict__ cur,
+                                             double* __restrict__ prev, const BList& L, uint32_t t,
+                                             const wvb_coefficients_canonical* __restrict__ coeffs,
+                                             const WgGeom& g, double courant, double courant_sq) {
     int bad = 0;
-    if (t < L.n) {
+    {
         const long long off = L.off[t];
         const uint32_t meta = L.meta[t];
         const uint32_t inmesh = (meta >> META_PORTMASK_SHIFT) & 63u;
@@ -562,6 +561,31 @@ wg_boundary(const double* __restrict__ cur, double* __restrict__ prev, BList L,
         }
         bad |= classify_bad(ret);
         prev[off] = ret;
+    }
+    return bad;
+}
+
+// All three boundary classes in one launch: blocks [0, nb1) walk the 1-d list,
+// [nb1, nb1 + nb2) the 2-d list, the rest the 3-d list. Runs on its own stream
+// next to the air-node kernel: the two touch disjoint nodes of `prev` and only
+// read `cur`.
+constexpr int WG_BND_THREADS = 128;
+__global__ void __launch_bounds__(WG_BND_THREADS, 5)
+wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
+                BList L3, uint32_t nb1, uint32_t nb2,
+                const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g, double courant,
+                double courant_sq, int* __restrict__ flag) {
+    int bad = 0;
+    const uint32_t b = blockIdx.x;
+    if (b < nb1) {
+        const uint32_t t = b * WG_BND_THREADS + threadIdx.x;
+        if (t < L1.n) bad = boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
+    } else if (b < nb1 + nb2) {
+        const uint32_t t = (b - nb1) * WG_BND_THREADS + threadIdx.x;
+        if (t < L2.n) bad = boundary_node<2>(cur, prev, L2, t, coeffs, g, courant, courant_sq);
+    } else {
+        const uint32_t t = (b - nb1 - nb2) * WG_BND_THREADS + threadIdx.x;
+        if (t < L3.n) bad = boundary_node<3>(cur, prev, L3, t, coeffs, g, courant, courant_sq);
     }
     raise_flags(bad, flag);
 }
