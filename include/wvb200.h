@@ -239,7 +239,114 @@ wvb_status wvb_wg_get_info(wvb_wg* wg, wvb_wg_info* info);
 wvb_status wvb_mesh_cuboid(const int32_t dim[3], int32_t z0, int32_t nz,
                            wvb_condensed_node* nodes_out, uint64_t counts[3]);
 
+/* ---- ray tracer ------------------------------------------------------------ */
+
+typedef struct wvb_rt wvb_rt;
+
+/* core::triangle, 16 B.  src/core/include/core/cl/triangle.h:8-13 */
+typedef struct {
+    uint32_t surface, v0, v1, v2;
+} wvb_triangle;
+/* cl_float3 is 16 bytes */
+typedef struct {
+    float x, y, z, w;
+} wvb_float3;
+/* core::surface<8>, 64 B.  src/core/include/core/cl/scene_structs.h:24-30 */
+typedef struct {
+    float absorption[8];
+    float scattering[8];
+} wvb_surface;
+/* raytracer::reflection, 32 B.  src/raytracer/include/raytracer/cl/reflection.h:10-17 */
+typedef struct {
+    wvb_float3 position;
+    uint32_t triangle;
+    int8_t keep_going;
+    int8_t receiver_visible;
+    int8_t pad_[10];
+} wvb_reflection;
+
+/* What core::scene_buffers uploads (spatial_division/scene_buffers.h:14-38) from a
+ * voxelised_scene_data: the flattened voxel index of voxel_collection.cpp:9-37
+ * (index[x*side*side + y*side + z] = offset of a run [count, tri, tri, ...]),
+ * the voxel grid's AABB and side, triangles, vertices and surfaces. */
+typedef struct {
+    const uint32_t* voxel_index;
+    uint64_t voxel_index_count;
+    float aabb_min[3], aabb_max[3];
+    uint32_t side;
+    const wvb_triangle* triangles;
+    uint32_t num_triangles;
+    const wvb_float3* vertices;
+    uint32_t num_vertices;
+    const wvb_surface* surfaces;
+    uint32_t num_surfaces;
+    int32_t device;
+} wvb_rt_scene_desc;
+
+wvb_status wvb_rt_create(const wvb_rt_scene_desc* desc, wvb_rt** out);
+void wvb_rt_destroy(wvb_rt* rt);
+
+/* One call = raytracer::run's segment loop (raytracer.h:223-262) for n_rays rays
+ * with the stochastic histogram processor folded in:
+ *   per ray, `depth` times: reflections kernel (program.cpp:59-153) + stochastic
+ *   kernel (stochastic/program.cpp:58-152) + binning by floor(distance / c * rate)
+ *   (stochastic_histogram.h:17-32,84-110). Specular ("intersected") impulses are
+ *   binned when step >= specular_from_step (the histogram processor's
+ *   max_image_source_order, canonical.cpp:9-20 passes order + 1).
+ * total_rays: N of compute_ray_energy (finder.h:18-25) -- all rays of the run,
+ * of which this call traces [ray_index_base, ray_index_base + n_rays).
+ * Random numbers: Philox4x32-10(seed; ray index, step) -- the reference seeds
+ * from std::random_device and is not reproducible (reflector.cpp:13-25).
+ * The histogram ACCUMULATES in device memory across calls with the same
+ * (n_bins, directional) until wvb_rt_reset_histogram(); layout [n_bins][8]
+ * doubles, or [20][9][n_bins][8] when directional (vector_look_up_table<..,20,9>).
+ * Impulses at or beyond n_bins are counted in *dropped. */
+typedef struct {
+    float source[3];
+    float receiver[3];
+    float receiver_radius;
+    float pad0_;
+    double speed_of_sound;
+    double histogram_sample_rate;
+    uint64_t total_rays;
+    uint64_t seed;
+    uint64_t ray_index_base;
+    uint32_t depth;
+    uint32_t specular_from_step;
+    uint32_t n_bins;
+    uint32_t directional;
+    uint32_t keep_steps; /* reflections of steps < keep_steps are returned (image-source / visual consumers) */
+    uint32_t pad1_;
+} wvb_rt_trace_params;
+
+/* directions: n_rays x 3 floats on the host (the iterator range raytracer::run
+ * receives), or NULL to generate sphere_point(z, theta) from Philox stream 1.
+ * reflections: [keep_steps][n_rays] records, or NULL. device_ms (optional):
+ * CUDA-event time of the trace kernel. */
+wvb_status wvb_rt_trace(wvb_rt* rt, const wvb_rt_trace_params* params, const float* directions,
+                        uint64_t n_rays, wvb_reflection* reflections, uint64_t* dropped,
+                        float* device_ms);
+wvb_status wvb_rt_read_histogram(wvb_rt* rt, double* out);
+wvb_status wvb_rt_reset_histogram(wvb_rt* rt);
+
+/* host helpers of the ray path */
+/* compute_optimum_reflection_number (optimum_reflection_number.h:38-40) */
+uint32_t wvb_rt_reflection_depth(double min_absorption);
+/* compute_ray_energy (stochastic/finder.cpp:7-15) */
+float wvb_rt_ray_energy(uint64_t total_rays, const float source[3], const float receiver[3],
+                        float receiver_radius);
+/* histogram length that cannot overflow: (depth + 1) segments of at most the
+ * voxel grid's diagonal */
+uint32_t wvb_rt_safe_bins(const wvb_rt* rt, uint32_t depth, double speed_of_sound, double rate);
+
 /* ---- test hooks ------------------------------------------------------------- */
+/* closest hit of n rays given as (position xyz, direction xyz); tri = ~0 for none.
+ * Mirrors the comparison of src/raytracer/tests/reflector_tests.cpp:98-154. */
+wvb_status wvb_rt_closest_hit(wvb_rt* rt, const float* rays6, uint64_t n, uint32_t* tri_out,
+                              float* t_out);
+/* the generated initial directions (Philox stream 1), n x 3 floats */
+wvb_status wvb_rt_directions(wvb_rt* rt, uint64_t seed, uint64_t base, uint64_t n, float* out3);
+
 /* Device evaluation of the kernels' division-by-3 (FMA-corrected reciprocal
  * multiply, csrc/wg_kernels.cuh third<true>) next to the IEEE `x / 3.0`, for n
  * host doubles; the two outputs must be bit-identical. Runs on the current

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(decl):
         assert hasattr(L, name), "libwvb200.so does not export " + name
     assert L.wvb_version() == 100
-    for name in _lib.WG_SYMBOLS:
+    for name in _lib.WG_SYMBOLS + _lib.RT_SYMBOLS:
         assert name in decl
 
 
@@ -89,6 +89,21 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.WvbError) as e:
         wvb.Waveguide(m)
     assert e.value.status in (_lib.WVB_ERR_NO_DEVICE, _lib.WVB_ERR_CUDA)
+
+
+def test_rt_host_helpers_and_validation():
+    from wayverb_b200 import scene
+    from oracle import rto
+    # compute_optimum_reflection_number: ceil(-6 / log10(1 - a)); 132 for a = 0.1
+    assert wvb.reflection_depth(0.1) == 132
+    src, rcv = [1.0, 1.0, 1.0], [2.0, 3.0, 1.5]
+    assert wvb.raytracer.ray_energy(1000, src, rcv, 0.1) == rto.ray_energy(1000, src, rcv, 0.1)
+    sc = scene.box_scene(subdiv=1, side=4)
+    bad = scene.Scene(sc.vertices[:, :3], sc.triangles, sc.surfaces, side=4)
+    bad.triangles["v0"][0] = 10_000
+    with pytest.raises(_lib.WvbError) as e:
+        wvb.RayTracer(bad)
+    assert e.value.status == _lib.WVB_ERR_INVALID
 
 
 def test_create_validates_description():

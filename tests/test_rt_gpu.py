@@ -1,0 +1,144 @@
+"""GPU parity tests of the ray path, through the C ABI, against the CPU oracle.
+
+All ray arithmetic is fp32 in the reference's operation order with FMA
+contraction off on both sides, and the random numbers / sincos are the shared
+fixed definitions, so hits, visibility flags and reflection points must be
+IDENTICAL (the reference's own GPU-vs-CPU bound is 1e-5 on positions,
+reflector_tests.cpp:122,145). Histograms are accumulated with fp64 atomics whose
+order is not fixed: tolerance 1e-9 relative to the largest bin (BASELINE's
+statistical criterion is 10 % per band / 1 % total)."""
+import numpy as np
+import pytest
+
+import wayverb_b200 as wvb
+from wayverb_b200 import scene
+from oracle import rto
+
+pytestmark = pytest.mark.gpu
+
+SRC = np.array([2.09, 2.12, 2.12], np.float32)
+RCV = np.array([2.09, 1.08, 0.96], np.float32)
+BOX = (4.0, 3.0, 6.0)
+
+
+def room(scatter, subdiv=2, side=8, absorption=0.1, per_wall=False):
+    surfs = [scene.make_surface(absorption, scatter)]
+    if per_wall:
+        surfs = [scene.make_surface(0.05 + 0.05 * k, [scatter * (1 + 0.1 * b) for b in range(8)]) for k in range(3)]
+    return scene.box_scene(BOX, subdiv=subdiv, side=side, surfaces=surfs, per_wall_surfaces=per_wall)
+
+
+def assert_hist_close(got, want):
+    scale = np.abs(want).max()
+    assert scale > 0
+    assert np.abs(got - want).max() <= 1e-9 * scale
+
+
+def test_generated_directions_identical():
+    with wvb.RayTracer(room(0.1)) as g:
+        assert np.array_equal(g.directions(1234, 100000), rto.directions(1234, 100000))
+        assert np.array_equal(g.directions(1234, 1000, base=77), rto.directions(1234, 1000, base=77))
+
+
+@pytest.mark.parametrize("subdiv,side", [(1, 4), (4, 8), (8, 32)])
+def test_closest_hit_matches_cpu_twins(subdiv, side):
+    sc = room(0.1, subdiv, side)
+    o = rto.Scene(sc)
+    n = 20000
+    rng = np.random.default_rng(5)
+    pos = (rng.uniform(0.05, 0.95, (n, 3)) * np.array(BOX)).astype(np.float32)
+    d = rto.directions(7, n)
+    with wvb.RayTracer(sc) as g:
+        tri_g, t_g = g.closest_hit(pos, d)
+    tri_v, t_v = o.closest_hit(pos, d, brute=False)
+    tri_b, t_b = o.closest_hit(pos, d, brute=True)
+    assert np.array_equal(tri_g, tri_v) and np.array_equal(t_g, t_v)
+    assert np.array_equal(tri_g, tri_b) and np.array_equal(t_g, t_b)
+
+
+@pytest.mark.parametrize("scatter", [0.0, 0.1, 0.6])
+@pytest.mark.parametrize("per_wall", [False, True])
+def test_trace_reflections_and_histogram(scatter, per_wall):
+    sc = room(scatter, subdiv=3, side=8, per_wall=per_wall)
+    o = rto.Scene(sc)
+    n, depth, keep = 30000, 40, 8
+    d = rto.directions(99, n)
+    want_h, want_r, want_drop = o.trace(d, SRC, RCV, depth, seed=5, specular_from_step=2, keep_steps=keep)
+    with wvb.RayTracer(sc) as g:
+        refl, dropped, ms = g.trace(d, SRC, RCV, depth, seed=5, specular_from_step=2, keep_steps=keep)
+        got_h = g.histogram()
+    assert dropped == want_drop == 0
+    assert got_h.shape == want_h.shape
+    for f in ("triangle", "keep_going", "receiver_visible"):
+        assert np.array_equal(refl[f], want_r[f]), f
+    assert np.array_equal(refl["position"], want_r["position"])
+    assert_hist_close(got_h, want_h)
+    assert ms > 0
+
+
+def test_device_generated_directions_and_segments_accumulate():
+    # two calls with ray_index_base == one call (raytracer.h:246-262 segments + accumulate)
+    sc = room(0.3, subdiv=2, side=8)
+    o = rto.Scene(sc)
+    n, depth = 20000, 30
+    d = rto.directions(42, n)
+    want_h, _, _ = o.trace(d, SRC, RCV, depth, seed=42)
+    with wvb.RayTracer(sc) as g:
+        bins = g.safe_bins(depth)
+        g.trace(None, SRC, RCV, depth, n_rays=12000, total_rays=n, seed=42, n_bins=bins)
+        g.trace(None, SRC, RCV, depth, n_rays=8000, total_rays=n, seed=42, ray_index_base=12000, n_bins=bins)
+        got = g.histogram()
+        assert_hist_close(got, want_h)
+        g.reset_histogram()
+        assert not g.histogram().any()
+
+
+def test_directional_histogram():
+    sc = room(0.2, subdiv=2, side=8)
+    o = rto.Scene(sc)
+    n, depth = 20000, 25
+    d = rto.directions(3, n)
+    want, _, _ = o.trace(d, SRC, RCV, depth, directional=True)
+    with wvb.RayTracer(sc) as g:
+        g.trace(d, SRC, RCV, depth, directional=True)
+        got = g.histogram()
+    assert got.shape == want.shape == (20, 9) + want.shape[2:]
+    assert_hist_close(got.sum((0, 1)), want.sum((0, 1)))
+    # device atan2f/asinf vs host libm may flip a cell for a direction exactly on a
+    # boundary; allow a vanishing fraction of the energy to sit in a neighbouring cell
+    moved = np.abs(got - want).sum() / want.sum()
+    assert moved < 1e-3
+
+
+def test_open_scene_dead_rays():
+    sc = room(0.1, subdiv=1, side=4)
+    keep = np.ones(sc.triangles.size, bool)
+    keep[:2] = False
+    open_sc = scene.Scene(sc.vertices[:, :3], sc.triangles[keep], sc.surfaces, side=4)
+    d = rto.directions(8, 20000)
+    want_h, want_r, _ = rto.Scene(open_sc).trace(d, SRC, RCV, 12, keep_steps=12)
+    with wvb.RayTracer(open_sc) as g:
+        refl, _, _ = g.trace(d, SRC, RCV, 12, keep_steps=12)
+        got_h = g.histogram()
+    assert not want_r["keep_going"].all()
+    assert np.array_equal(refl["keep_going"], want_r["keep_going"])
+    assert np.array_equal(refl["position"], want_r["position"])
+    assert_hist_close(got_h, want_h)
+
+
+def test_config5_sized_run_statistics():
+    """1 M rays in a many-triangle room (config 5's ray count): energy bookkeeping must
+    agree with an independent 64 k-ray oracle run within the reference's statistical
+    criterion (10 % per band in the summed histogram, equal_energy.cpp:88)."""
+    sc = scene.box_scene((12.0, 8.0, 20.0), subdiv=12, side=16,
+                         surfaces=[scene.make_surface([0.1, 0.1, 0.12, 0.15, 0.2, 0.25, 0.3, 0.35], 0.3)])
+    src, rcv = [3.0, 2.0, 4.0], [8.0, 5.0, 15.0]
+    depth = 60
+    with wvb.RayTracer(sc) as g:
+        _, dropped, ms = g.trace(None, src, rcv, depth, n_rays=1 << 20, seed=9)
+        big = g.histogram()
+    assert dropped == 0 and np.isfinite(big).all() and (big >= 0).all()
+    small, _, _ = rto.Scene(sc).trace(rto.directions(1234, 1 << 16), src, rcv, depth, seed=77)
+    per_band_big, per_band_small = big.sum(0), small.sum(0)
+    assert np.abs(per_band_big / per_band_small - 1).max() < 0.10
+    assert abs(big.sum() / small.sum() - 1) < 0.02

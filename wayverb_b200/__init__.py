@@ -9,5 +9,8 @@ from . import _lib  # noqa: F401
 from .waveguide import (Mesh, Waveguide, cuboid_mesh, hard_source, soft_source, node_receiver,  # noqa: F401
                         run, slab_range)
 
-__all__ = ["Mesh", "Waveguide", "cuboid_mesh", "hard_source", "soft_source", "node_receiver", "run",
+from .raytracer import RayTracer, reflection_depth  # noqa: F401,E402
+from . import scene  # noqa: F401,E402
+
+__all__ = ["RayTracer", "reflection_depth", "scene", "Mesh", "Waveguide", "cuboid_mesh", "hard_source", "soft_source", "node_receiver", "run",
            "slab_range"]

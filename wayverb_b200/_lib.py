@@ -63,6 +63,28 @@ class WgInfo(C.Structure):
     ]
 
 
+class RtSceneDesc(C.Structure):
+    _fields_ = [
+        ("voxel_index", C.c_void_p), ("voxel_index_count", C.c_uint64),
+        ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("side", C.c_uint32),
+        ("triangles", C.c_void_p), ("num_triangles", C.c_uint32),
+        ("vertices", C.c_void_p), ("num_vertices", C.c_uint32),
+        ("surfaces", C.c_void_p), ("num_surfaces", C.c_uint32),
+        ("device", C.c_int32),
+    ]
+
+
+class RtTraceParams(C.Structure):
+    _fields_ = [
+        ("source", C.c_float * 3), ("receiver", C.c_float * 3),
+        ("receiver_radius", C.c_float), ("pad0", C.c_float),
+        ("speed_of_sound", C.c_double), ("histogram_sample_rate", C.c_double),
+        ("total_rays", C.c_uint64), ("seed", C.c_uint64), ("ray_index_base", C.c_uint64),
+        ("depth", C.c_uint32), ("specular_from_step", C.c_uint32), ("n_bins", C.c_uint32),
+        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("pad1", C.c_uint32),
+    ]
+
+
 # every symbol include/wvb200.h declares (tests check the .so exports them all)
 WG_SYMBOLS = [
     "wvb_wg_create", "wvb_wg_destroy", "wvb_wg_write_f64", "wvb_wg_read_f64", "wvb_wg_read_field",
@@ -71,6 +93,12 @@ WG_SYMBOLS = [
     "wvb_wg_boundary_count", "wvb_wg_read_boundary_data", "wvb_wg_time_steps", "wvb_wg_time_kernels",
     "wvb_wg_get_info", "wvb_nccl_unique_id", "wvb_test_third",
     "wvb_mesh_cuboid", "wvb_version", "wvb_device_count", "wvb_last_error",
+]
+
+RT_SYMBOLS = [
+    "wvb_rt_create", "wvb_rt_destroy", "wvb_rt_trace", "wvb_rt_read_histogram", "wvb_rt_reset_histogram",
+    "wvb_rt_reflection_depth", "wvb_rt_ray_energy", "wvb_rt_safe_bins", "wvb_rt_closest_hit",
+    "wvb_rt_directions",
 ]
 
 _lib = None
@@ -115,6 +143,20 @@ def lib():
     L.wvb_nccl_unique_id.argtypes = [vp, C.c_size_t]
     L.wvb_wg_get_info.argtypes = [vp, C.POINTER(WgInfo)]
     L.wvb_mesh_cuboid.argtypes = [C.POINTER(i32 * 3), i32, i32, vp, C.POINTER(u64 * 3)]
+    L.wvb_rt_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(vp)]
+    L.wvb_rt_destroy.argtypes = [vp]
+    L.wvb_rt_destroy.restype = None
+    L.wvb_rt_trace.argtypes = [vp, C.POINTER(RtTraceParams), vp, u64, vp, C.POINTER(u64), C.POINTER(C.c_float)]
+    L.wvb_rt_read_histogram.argtypes = [vp, vp]
+    L.wvb_rt_reset_histogram.argtypes = [vp]
+    L.wvb_rt_reflection_depth.restype = u32
+    L.wvb_rt_reflection_depth.argtypes = [C.c_double]
+    L.wvb_rt_ray_energy.restype = C.c_float
+    L.wvb_rt_ray_energy.argtypes = [u64, vp, vp, C.c_float]
+    L.wvb_rt_safe_bins.restype = u32
+    L.wvb_rt_safe_bins.argtypes = [vp, u32, C.c_double, C.c_double]
+    L.wvb_rt_closest_hit.argtypes = [vp, vp, u64, vp, vp]
+    L.wvb_rt_directions.argtypes = [vp, u64, u64, u64, vp]
     _lib = L
     return L
 

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     # keep the reference's operation order: no FMA contraction, IEEE div/sqrt
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
 ]
 
 

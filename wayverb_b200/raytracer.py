@@ -1,0 +1,118 @@
+"""Host mirror of the reference's ray-tracing interface over the C ABI.
+
+  RayTracer(scene)            core::scene_buffers + the per-run state of raytracer::run
+                              (raytracer.h:188-266)
+  RayTracer.trace(...)        the segment x depth loop with the stochastic histogram
+                              processor (reflection_processor/stochastic_histogram.h) folded in;
+                              reflections of the first `keep_steps` steps are what the
+                              image-source / visual processors consume
+  reflection_depth(...)       compute_optimum_reflection_number (optimum_reflection_number.h:38-40)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import RtSceneDesc, RtTraceParams, check, lib, ptr
+from .scene import REFL_DT, Scene
+
+
+def reflection_depth(min_absorption: float) -> int:
+    return int(lib().wvb_rt_reflection_depth(float(min_absorption)))
+
+
+def ray_energy(total_rays, source, receiver, radius) -> float:
+    s = np.asarray(source, np.float32)
+    r = np.asarray(receiver, np.float32)
+    return float(lib().wvb_rt_ray_energy(int(total_rays), ptr(s), ptr(r), float(radius)))
+
+
+class RayTracer:
+    def __init__(self, scene: Scene, device=0):
+        self.scene = scene
+        d = RtSceneDesc()
+        d.voxel_index = scene.voxel_index.ctypes.data
+        d.voxel_index_count = scene.voxel_index.size
+        d.aabb_min[:] = [float(v) for v in scene.aabb[:3]]
+        d.aabb_max[:] = [float(v) for v in scene.aabb[3:]]
+        d.side = scene.side
+        d.triangles = scene.triangles.ctypes.data
+        d.num_triangles = scene.triangles.size
+        d.vertices = scene.vertices.ctypes.data
+        d.num_vertices = scene.vertices.shape[0]
+        d.surfaces = scene.surfaces.ctypes.data
+        d.num_surfaces = scene.surfaces.size
+        d.device = int(device)
+        h = C.c_void_p()
+        check(lib().wvb_rt_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._shape = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().wvb_rt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def safe_bins(self, depth, speed_of_sound=340.0, rate=1000.0) -> int:
+        return int(lib().wvb_rt_safe_bins(self._h, int(depth), float(speed_of_sound), float(rate)))
+
+    def trace(self, dirs, source, receiver, depth, n_rays=None, total_rays=None, receiver_radius=0.1,
+              speed_of_sound=340.0, histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0,
+              n_bins=None, directional=False, keep_steps=0):
+        """dirs: n x 3 float32 or None (generate n_rays directions on the device).
+        Returns (reflections or None, dropped, device_ms); the histogram accumulates on the
+        device, read it with histogram()."""
+        if dirs is not None:
+            d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+            n = d.shape[0]
+        else:
+            d, n = None, int(n_rays)
+        P = RtTraceParams()
+        P.source[:] = [float(v) for v in source]
+        P.receiver[:] = [float(v) for v in receiver]
+        P.receiver_radius = receiver_radius
+        P.speed_of_sound, P.histogram_sample_rate = speed_of_sound, histogram_rate
+        P.total_rays = n if total_rays is None else int(total_rays)
+        P.seed, P.ray_index_base = int(seed), int(ray_index_base)
+        P.depth, P.specular_from_step = int(depth), int(specular_from_step)
+        P.n_bins = self.safe_bins(depth, speed_of_sound, histogram_rate) if n_bins is None else int(n_bins)
+        P.directional, P.keep_steps = int(bool(directional)), int(keep_steps)
+        self._shape = (20, 9, P.n_bins, 8) if directional else (P.n_bins, 8)
+        refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
+        dropped, ms = C.c_uint64(0), C.c_float(0)
+        check(lib().wvb_rt_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n,
+                                 ptr(refl) if refl is not None else None, C.byref(dropped), C.byref(ms)))
+        return refl, dropped.value, ms.value
+
+    def histogram(self) -> np.ndarray:
+        out = np.zeros(self._shape)
+        check(lib().wvb_rt_read_histogram(self._h, ptr(out)))
+        return out
+
+    def reset_histogram(self):
+        check(lib().wvb_rt_reset_histogram(self._h))
+
+    def closest_hit(self, pos, dirs):
+        rays = np.ascontiguousarray(np.concatenate([pos, dirs], 1), np.float32)
+        n = rays.shape[0]
+        tri, t = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        check(lib().wvb_rt_closest_hit(self._h, ptr(rays), n, ptr(tri), ptr(t)))
+        return tri, t
+
+    def directions(self, seed, n, base=0):
+        out = np.zeros((n, 3), np.float32)
+        check(lib().wvb_rt_directions(self._h, int(seed), int(base), int(n), ptr(out)))
+        return out
