@@ -94,6 +94,7 @@ struct wvb_wg {
     cudaStream_t stream_b = nullptr;  // boundary kernel runs here, next to the air kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
+    int bminb = 5;
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
     int ty = 8, nstage = 5, zchunks = 1;
@@ -319,9 +320,15 @@ void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st
         auto& l = w->bl[k];
         return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
     };
-    wg_boundary_all<<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
-                                                      w->coeffs.p, w->g, w->courant, w->courant_sq,
-                                                      w->flag.p);
+    if (w->bminb >= 8) {
+        wg_boundary_all<8><<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
+                                                          w->coeffs.p, w->g, w->courant,
+                                                          w->courant_sq, w->flag.p);
+    } else {
+        wg_boundary_all<5><<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
+                                                          w->coeffs.p, w->g, w->courant,
+                                                          w->courant_sq, w->flag.p);
+    }
     w->launches++;
 }
 
@@ -547,6 +554,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
+    w->bminb = env_int("WVB_WG_BMINB", 5);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);

@@ -570,7 +570,8 @@ __device__ __forceinline__ int boundary_node(const double* __restrict__ cur,
 // next to the air-node kernel: the two touch disjoint nodes of `prev` and only
 // read `cur`.
 constexpr int WG_BND_THREADS = 128;
-__global__ void __launch_bounds__(WG_BND_THREADS, 5)
+template <int MINB>
+__global__ void __launch_bounds__(WG_BND_THREADS, MINB)
 wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
                 BList L3, uint32_t nb1, uint32_t nb2,
                 const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g, double courant,
