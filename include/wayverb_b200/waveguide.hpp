@@ -1,0 +1,448 @@
+// waveguide.hpp -- C++14 shim that keeps the reference's `waveguide::run` entry
+// point and the types it takes, on top of the C ABI of libwvb200.so.
+//
+//   reference                                            here
+//   src/waveguide/include/waveguide/waveguide.h:36-126    wayverb::waveguide::run
+//   .../waveguide/mesh.h:12-26, setup.h:27-85             mesh, vectors
+//   .../waveguide/mesh_descriptor.h:14-20                 mesh_descriptor (+ compute_index/locator)
+//   .../waveguide/cl/structs.h, filter_structs.h          condensed_node, coefficients_canonical, ...
+//   src/core/include/core/cl/common.h:13-57               core::compute_context, read_value, write_value,
+//                                                         read_from_buffer, items_in_buffer
+//   .../waveguide/preprocessor/{hard,soft}_source.h       preprocessor::make_hard_source / make_soft_source
+//   .../waveguide/postprocessor/node.h                    postprocessor::node
+//   src/core/include/core/exceptions.h:22-30              core::exceptions::value_is_inf / value_is_nan
+//
+// Everything is header-only; link with -lwvb200. The per-step order of effects
+// is the reference's: pre -> flag reset -> kernel -> flag check/throw -> post ->
+// swap. Pressures are fp64 on the device; `read_value<cl_float>` and friends
+// convert, so callers that keep float (e.g. directional_receiver) are unchanged.
+#pragma once
+
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../wvb200.h"
+#include "cl_compat.hpp"
+
+namespace util {
+namespace aligned {
+template <typename T>
+using vector = std::vector<T>;  // utilities/aligned/vector.h: std::vector with an aligned allocator
+}  // namespace aligned
+}  // namespace util
+
+namespace wayverb {
+namespace core {
+
+enum class device_type { cpu, gpu };
+
+/// cl::Context + cl::Device in the reference (cl/common.h:13-22); here a CUDA
+/// device ordinal. There is no CPU device: device_type::cpu is refused.
+class compute_context final {
+public:
+    compute_context() = default;
+    explicit compute_context(int cuda_device) : device{cuda_device} {}
+    explicit compute_context(device_type type) {
+        if (type != device_type::gpu) {
+            throw std::runtime_error{"wayverb_b200 has no CPU path: a B200 is required."};
+        }
+    }
+    int device{0};
+};
+
+namespace exceptions {
+struct value_is_nan final : public std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct value_is_inf final : public std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+}  // namespace exceptions
+
+namespace detail {
+inline void check(wvb_status s) {
+    if (s != WVB_OK && s != WVB_ERR_SIM) {
+        throw std::runtime_error{std::string{"libwvb200: "} + wvb_last_error()};
+    }
+}
+}  // namespace detail
+
+template <typename T>
+size_t items_in_buffer(const cl::Buffer& buffer) {
+    return buffer.items();
+}
+
+template <typename T>
+T read_value(cl::CommandQueue&, const cl::Buffer& buffer, size_t index) {
+    double v = 0;
+    detail::check(wvb_wg_read_f64(buffer.handle(), index, &v, nullptr));
+    return static_cast<T>(v);
+}
+
+template <typename T>
+void write_value(cl::CommandQueue&, cl::Buffer& buffer, size_t index, T val) {
+    detail::check(wvb_wg_write_f64(buffer.handle(), index, static_cast<double>(val)));
+}
+
+template <typename T>
+util::aligned::vector<T> read_from_buffer(cl::CommandQueue&, const cl::Buffer& buffer);
+
+template <>
+inline util::aligned::vector<double> read_from_buffer<double>(cl::CommandQueue&,
+                                                              const cl::Buffer& buffer) {
+    util::aligned::vector<double> ret(buffer.items());
+    detail::check(wvb_wg_read_field(buffer.handle(), ret.data()));
+    return ret;
+}
+template <>
+inline util::aligned::vector<float> read_from_buffer<float>(cl::CommandQueue&,
+                                                            const cl::Buffer& buffer) {
+    util::aligned::vector<float> ret(buffer.items());
+    detail::check(wvb_wg_read_field_f32(buffer.handle(), ret.data()));
+    return ret;
+}
+
+/// callback_accumulator (core/callback_accumulator.h): collects what a
+/// postprocessor returns each step.
+template <typename Callback>
+class callback_accumulator final {
+public:
+    template <typename... Ts>
+    explicit callback_accumulator(Ts&&... ts) : callback_{std::forward<Ts>(ts)...} {}
+    template <typename... Ts>
+    void operator()(Ts&&... ts) {
+        output_.emplace_back(callback_(std::forward<Ts>(ts)...));
+    }
+    const auto& get_output() const { return output_; }
+    const Callback& get_callback() const { return callback_; }
+
+private:
+    Callback callback_;
+    util::aligned::vector<typename Callback::return_type> output_;
+};
+
+}  // namespace core
+
+namespace waveguide {
+
+// ---- PODs: the layouts are the contract (see include/wvb200.h for file:line) ----
+using error_code = cl_int;
+constexpr cl_int id_success = 0, id_inf_error = 1 << 0, id_nan_error = 1 << 1,
+                 id_outside_range_error = 1 << 2, id_outside_mesh_error = 1 << 3,
+                 id_suspicious_boundary_error = 1 << 4;
+using boundary_type = cl_int;
+constexpr cl_int id_none = 0, id_inside = 1 << 0, id_nx = 1 << 1, id_px = 1 << 2, id_ny = 1 << 3,
+                 id_py = 1 << 4, id_nz = 1 << 5, id_pz = 1 << 6, id_reentrant = 1 << 7;
+constexpr auto no_neighbor = ~cl_uint{0};
+constexpr size_t biquad_order{2}, biquad_sections{3};
+using filt_real = cl_double;
+
+struct alignas(8) condensed_node final {
+    cl_int boundary_type{};
+    cl_uint boundary_index{};
+};
+template <size_t o>
+struct alignas(8) coefficients final {
+    static constexpr auto order = o;
+    filt_real b[order + 1]{};
+    filt_real a[order + 1]{};
+};
+using coefficients_canonical = coefficients<biquad_order * biquad_sections>;
+template <size_t n>
+struct alignas(4) boundary_index_array final {
+    cl_uint array[n];
+};
+using boundary_index_array_1 = boundary_index_array<1>;
+using boundary_index_array_2 = boundary_index_array<2>;
+using boundary_index_array_3 = boundary_index_array<3>;
+struct boundary_index_data final {
+    util::aligned::vector<boundary_index_array_1> b1;
+    util::aligned::vector<boundary_index_array_2> b2;
+    util::aligned::vector<boundary_index_array_3> b3;
+};
+static_assert(sizeof(condensed_node) == sizeof(wvb_condensed_node), "condensed_node layout");
+static_assert(sizeof(coefficients_canonical) == sizeof(wvb_coefficients_canonical),
+              "coefficients_canonical layout");
+
+struct alignas(16) mesh_descriptor final {
+    static constexpr auto no_neighbor = ~cl_uint{0};
+    cl_float3 min_corner;
+    cl_int3 dimensions;
+    cl_float spacing;
+};
+static_assert(sizeof(mesh_descriptor) == 48, "mesh_descriptor layout (SURVEY 8a)");
+
+inline size_t compute_num_nodes(const mesh_descriptor& d) {
+    return size_t(d.dimensions.s[0]) * size_t(d.dimensions.s[1]) * size_t(d.dimensions.s[2]);
+}
+/// compute_index (mesh_descriptor.cpp:7-10): x fastest
+inline size_t compute_index(const mesh_descriptor& d, int x, int y, int z) {
+    return size_t(x) + size_t(y) * d.dimensions.s[0] +
+           size_t(z) * d.dimensions.s[0] * size_t(d.dimensions.s[1]);
+}
+/// compute_locator (mesh_descriptor.cpp:16-20)
+inline std::array<int, 3> compute_locator(const mesh_descriptor& d, size_t index) {
+    const size_t dx = d.dimensions.s[0], dy = d.dimensions.s[1], dz = d.dimensions.s[2];
+    return {{int(index % dx), int((index / dx) % dy), int((index / dx / dy) % dz)}};
+}
+
+constexpr bool is_inside(const condensed_node& c) { return c.boundary_type & id_inside; }
+
+class vectors final {
+public:
+    vectors(util::aligned::vector<condensed_node> nodes,
+            util::aligned::vector<coefficients_canonical> coefficients,
+            boundary_index_data boundary_index_data)
+            : condensed_nodes_(std::move(nodes))
+            , coefficients_(std::move(coefficients))
+            , boundary_index_data_(std::move(boundary_index_data)) {}
+
+    template <size_t n>
+    const util::aligned::vector<boundary_index_array<n>>& get_boundary_indices() const;
+    const util::aligned::vector<condensed_node>& get_condensed_nodes() const {
+        return condensed_nodes_;
+    }
+    const util::aligned::vector<coefficients_canonical>& get_coefficients() const {
+        return coefficients_;
+    }
+    void set_coefficients(coefficients_canonical c) {
+        for (auto& i : coefficients_) i = c;
+    }
+    void set_coefficients(util::aligned::vector<coefficients_canonical> c) {
+        if (c.size() != coefficients_.size()) {
+            throw std::runtime_error(
+                    "Size of new coefficients vector must be equal to the existing one in order "
+                    "to maintain object invariants.");
+        }
+        coefficients_ = std::move(c);
+    }
+
+private:
+    util::aligned::vector<condensed_node> condensed_nodes_;
+    util::aligned::vector<coefficients_canonical> coefficients_;
+    boundary_index_data boundary_index_data_;
+};
+template <>
+inline const util::aligned::vector<boundary_index_array<1>>& vectors::get_boundary_indices<1>() const {
+    return boundary_index_data_.b1;
+}
+template <>
+inline const util::aligned::vector<boundary_index_array<2>>& vectors::get_boundary_indices<2>() const {
+    return boundary_index_data_.b2;
+}
+template <>
+inline const util::aligned::vector<boundary_index_array<3>>& vectors::get_boundary_indices<3>() const {
+    return boundary_index_data_.b3;
+}
+
+class mesh final {
+public:
+    mesh(mesh_descriptor descriptor, vectors vectors)
+            : descriptor_(descriptor), vectors_(std::move(vectors)) {}
+    const mesh_descriptor& get_descriptor() const { return descriptor_; }
+    const vectors& get_structure() const { return vectors_; }
+    void set_coefficients(coefficients_canonical c) { vectors_.set_coefficients(c); }
+    void set_coefficients(util::aligned::vector<coefficients_canonical> c) {
+        vectors_.set_coefficients(std::move(c));
+    }
+
+private:
+    mesh_descriptor descriptor_;
+    vectors vectors_;
+};
+
+inline bool is_inside(const mesh& m, size_t node_index) {
+    return is_inside(m.get_structure().get_condensed_nodes()[node_index]);
+}
+
+/// Synthetic box room through wvb_mesh_cuboid (what compute_mesh, mesh.cpp:53-141,
+/// yields for a cuboid), one surface.
+inline mesh make_cuboid_mesh(int dx, int dy, int dz, float spacing, coefficients_canonical c) {
+    mesh_descriptor d{};
+    d.dimensions.s[0] = dx; d.dimensions.s[1] = dy; d.dimensions.s[2] = dz;
+    d.spacing = spacing;
+    util::aligned::vector<condensed_node> nodes(size_t(dx) * dy * dz);
+    const int32_t dim[3] = {dx, dy, dz};
+    uint64_t counts[3] = {0, 0, 0};
+    core::detail::check(wvb_mesh_cuboid(dim, 0, dz, reinterpret_cast<wvb_condensed_node*>(nodes.data()),
+                                        counts));
+    boundary_index_data b;
+    b.b1.assign(counts[0], boundary_index_array_1{{0}});
+    b.b2.assign(counts[1], boundary_index_array_2{{0, 0}});
+    b.b3.assign(counts[2], boundary_index_array_3{{0, 0, 0}});
+    return mesh{d, vectors{std::move(nodes), {c}, std::move(b)}};
+}
+
+// ---- the entry point -------------------------------------------------------------------
+namespace detail {
+class handle final {
+public:
+    handle(const core::compute_context& cc, const mesh& m) {
+        const auto& v = m.get_structure();
+        wvb_wg_desc d{};
+        for (int i = 0; i < 3; ++i) d.dim[i] = m.get_descriptor().dimensions.s[i];
+        d.z_begin = 0;
+        d.z_end = d.dim[2];
+        d.nodes = reinterpret_cast<const wvb_condensed_node*>(v.get_condensed_nodes().data());
+        d.nodes_z0 = 0;
+        d.nodes_nz = d.dim[2];
+        d.coefficients =
+                reinterpret_cast<const wvb_coefficients_canonical*>(v.get_coefficients().data());
+        d.num_coefficients = uint32_t(v.get_coefficients().size());
+        d.boundary_index[0] = reinterpret_cast<const uint32_t*>(v.get_boundary_indices<1>().data());
+        d.boundary_index[1] = reinterpret_cast<const uint32_t*>(v.get_boundary_indices<2>().data());
+        d.boundary_index[2] = reinterpret_cast<const uint32_t*>(v.get_boundary_indices<3>().data());
+        d.boundary_count[0] = v.get_boundary_indices<1>().size();
+        d.boundary_count[1] = v.get_boundary_indices<2>().size();
+        d.boundary_count[2] = v.get_boundary_indices<3>().size();
+        d.device = cc.device;
+        d.rank = 0;
+        d.nranks = 1;
+        core::detail::check(wvb_wg_create(&d, &wg_));
+        if (!wg_) throw std::runtime_error{std::string{"libwvb200: "} + wvb_last_error()};
+    }
+    ~handle() { wvb_wg_destroy(wg_); }
+    handle(const handle&) = delete;
+    handle& operator=(const handle&) = delete;
+    wvb_wg* get() const { return wg_; }
+
+private:
+    wvb_wg* wg_{nullptr};
+};
+}  // namespace detail
+
+/// waveguide::run (waveguide.h:36-126).
+///   pre(cl::CommandQueue&, cl::Buffer&, size_t step) -> bool   (false ends the run)
+///   post(cl::CommandQueue&, const cl::Buffer&, size_t step)
+/// returns the number of steps completed; throws what the reference throws.
+template <typename step_preprocessor, typename step_postprocessor>
+size_t run(const core::compute_context& cc,
+           const mesh& mesh,
+           step_preprocessor&& pre,
+           step_postprocessor&& post,
+           const std::atomic_bool& keep_going) {
+    const detail::handle h{cc, mesh};
+    cl::CommandQueue queue{h.get()};
+    cl::Buffer current{h.get(), compute_num_nodes(mesh.get_descriptor())};
+
+    auto step = 0u;
+    for (; pre(queue, current, step) && keep_going; ++step) {
+        int32_t error_flag = 0;
+        core::detail::check(wvb_wg_launch(h.get(), &error_flag));
+        if (error_flag) {
+            if (error_flag & id_inf_error) {
+                throw core::exceptions::value_is_inf(
+                        "Pressure value is inf, check filter coefficients.");
+            }
+            if (error_flag & id_nan_error) {
+                throw core::exceptions::value_is_nan(
+                        "Pressure value is nan, check filter coefficients.");
+            }
+            if (error_flag & id_outside_mesh_error) {
+                throw std::runtime_error("Tried to read non-existant node.");
+            }
+            if (error_flag & id_suspicious_boundary_error) {
+                throw std::runtime_error("Suspicious boundary read.");
+            }
+        }
+        post(queue, static_cast<const cl::Buffer&>(current), step);
+        core::detail::check(wvb_wg_swap(h.get()));
+    }
+    return step;
+}
+
+/// The same loop for the stock processors, executed on the device in one call
+/// (wvb_wg_run): hard/soft source at one node, postprocessor::node at each
+/// receiver. out[step * receivers.size() + r].
+inline size_t run_stock(const core::compute_context& cc, const mesh& mesh, size_t source_node,
+                        const util::aligned::vector<double>& signal, bool soft,
+                        const util::aligned::vector<size_t>& receivers,
+                        util::aligned::vector<double>& out) {
+    const detail::handle h{cc, mesh};
+    util::aligned::vector<uint64_t> rcv(receivers.begin(), receivers.end());
+    out.assign(signal.size() * receivers.size(), 0.0);
+    wvb_wg_run_params p{};
+    p.source_node = source_node;
+    p.signal = signal.data();
+    p.n_steps = uint32_t(signal.size());
+    p.soft = soft ? 1 : 0;
+    p.receiver_nodes = rcv.data();
+    p.n_receivers = uint32_t(rcv.size());
+    p.out = out.data();
+    p.check_interval = 64;
+    uint32_t done = 0;
+    int32_t flags = 0;
+    core::detail::check(wvb_wg_run(h.get(), &p, &done, &flags));
+    if (flags & id_inf_error) throw core::exceptions::value_is_inf("Pressure value is inf, check filter coefficients.");
+    if (flags & id_nan_error) throw core::exceptions::value_is_nan("Pressure value is nan, check filter coefficients.");
+    if (flags & id_outside_mesh_error) throw std::runtime_error("Tried to read non-existant node.");
+    if (flags & id_suspicious_boundary_error) throw std::runtime_error("Suspicious boundary read.");
+    return done;
+}
+
+// ---- stock processors (same behaviour as the reference's) ---------------------------------
+namespace preprocessor {
+/// hard_source.h:9-37: overwrite the node with the next sample every step.
+template <typename It>
+class hard_source final {
+public:
+    hard_source(size_t node, It begin, It end) : node_{node}, begin_{begin}, end_{end} {}
+    bool operator()(cl::CommandQueue& queue, cl::Buffer& buffer, size_t) {
+        if (begin_ == end_) return false;
+        core::write_value(queue, buffer, node_, *begin_++);
+        return true;
+    }
+
+private:
+    size_t node_;
+    It begin_, end_;
+};
+template <typename It>
+auto make_hard_source(size_t node, It begin, It end) {
+    return hard_source<It>{node, begin, end};
+}
+/// soft_source.h:9-39: add the next sample to the node every step.
+template <typename It>
+class soft_source final {
+public:
+    soft_source(size_t node, It begin, It end) : node_{node}, begin_{begin}, end_{end} {}
+    bool operator()(cl::CommandQueue& queue, cl::Buffer& buffer, size_t) {
+        if (begin_ == end_) return false;
+        const auto current_pressure = core::read_value<cl_double>(queue, buffer, node_);
+        core::write_value(queue, buffer, node_, current_pressure + *begin_++);
+        return true;
+    }
+
+private:
+    size_t node_;
+    It begin_, end_;
+};
+template <typename It>
+auto make_soft_source(size_t node, It begin, It end) {
+    return soft_source<It>{node, begin, end};
+}
+}  // namespace preprocessor
+
+namespace postprocessor {
+/// node.cpp:14-18: the pressure at one node each step.
+class node final {
+public:
+    explicit node(size_t output_node) : output_node_{output_node} {}
+    using return_type = double;
+    return_type operator()(cl::CommandQueue& queue, const cl::Buffer& buffer, size_t) const {
+        return core::read_value<cl_double>(queue, buffer, output_node_);
+    }
+    size_t get_output_node() const { return output_node_; }
+
+private:
+    size_t output_node_;
+};
+}  // namespace postprocessor
+
+}  // namespace waveguide
+}  // namespace wayverb

@@ -1,0 +1,94 @@
+// Drives wayverb::raytracer::run (the shim of raytracer.h:188-266) the way
+// raytracer/canonical.h:44-75 does: random directions, image-source order 4,
+// directional histogram off/on, 32 visual rays; checks the protocol-level
+// behaviour (segments, per-step callback, keep_going, result shapes, energy).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+#include "wayverb_b200/raytracer.hpp"
+
+using namespace wayverb;
+
+static core::flattened_scene shoebox(float sx, float sy, float sz, unsigned side) {
+    core::flattened_scene s;
+    const float X[2] = {0, sx}, Y[2] = {0, sy}, Z[2] = {0, sz};
+    for (int i = 0; i < 8; ++i) s.vertices.push_back(cl_float3{{X[i & 1], Y[(i >> 1) & 1], Z[(i >> 2) & 1], 0}});
+    const unsigned q[6][4] = {{0, 1, 3, 2}, {4, 6, 7, 5}, {0, 4, 5, 1}, {2, 3, 7, 6}, {0, 2, 6, 4}, {1, 5, 7, 3}};
+    for (auto& f : q) {
+        s.triangles.push_back(core::triangle{0, f[0], f[1], f[2]});
+        s.triangles.push_back(core::triangle{0, f[0], f[2], f[3]});
+    }
+    core::surface<8> surf{};
+    for (int b = 0; b < 8; ++b) { surf.absorption.s[b] = 0.1f; surf.scattering.s[b] = 0.1f; }
+    s.surfaces.push_back(surf);
+    s.aabb_min = {-0.1f, -0.1f, -0.1f};
+    s.aabb_max = {sx + 0.1f, sy + 0.1f, sz + 0.1f};
+    s.side = side;
+    // every triangle in every voxel: a legal (if slow) superset assignment
+    const unsigned cells = side * side * side;
+    s.voxel_index.resize(cells);
+    for (unsigned c = 0; c < cells; ++c) {
+        s.voxel_index[c] = cl_uint(s.voxel_index.size());
+        s.voxel_index.push_back(cl_uint(s.triangles.size()));
+        for (unsigned t = 0; t < s.triangles.size(); ++t) s.voxel_index.push_back(t);
+    }
+    return s;
+}
+
+int main() {
+    const auto scene = shoebox(5.56f, 3.97f, 2.81f, 4);
+    const core::compute_context cc{};
+    const core::vec3 source{1, 1, 1}, receiver{2, 3, 1.5f};
+    std::mt19937 eng{7};
+    std::uniform_real_distribution<float> uz(-1, 1), ut(-3.14159265f, 3.14159265f);
+    const size_t rays = (1 << 15) + 1000;  // two full segments + a tail
+    std::vector<core::vec3> dirs(rays);
+    for (auto& d : dirs) {
+        const float z = uz(eng), th = ut(eng), t = std::sqrt(1 - z * z);
+        d = {t * std::cos(th), z, t * std::sin(th)};
+    }
+    int calls = 0;
+    auto res = raytracer::run(dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{},
+                              true, [&](auto group, auto groups) { calls += (groups == 2 && group == size_t(calls)); },
+                              4, 0.1f, 1000.0f, false, 32, 1234);
+    if (!res.completed || calls != 2) return 2;
+    if (raytracer::compute_optimum_reflection_number(scene) != 132) return 3;
+    if (res.first_reflections.size() != 4 || res.first_reflections[0].size() != rays) return 4;
+    if (res.visual.size() != 132 || res.visual[0].size() != 32) return 5;
+    for (auto& r : res.first_reflections[0]) {
+        if (!r.keep_going) return 6;  // closed box: nobody escapes
+    }
+    double total = 0;
+    for (auto& b : res.histogram.histogram) {
+        for (float v : b.s) {
+            if (!(v >= 0) || !std::isfinite(v)) return 7;
+            total += v;
+        }
+    }
+    if (!(total > 0) || res.histogram.histogram.empty() || res.dropped_impulses) return 8;
+
+    // directional run sums to the same energy
+    auto dres = raytracer::run(dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{},
+                               true, [](auto, auto) {}, 4, 0.1f, 1000.0f, true, 0, 1234);
+    double dtotal = 0;
+    for (auto& row : dres.directional.histogram.table) {
+        for (auto& cell : row) {
+            for (auto& b : cell) {
+                for (float v : b.s) dtotal += v;
+            }
+        }
+    }
+    if (std::fabs(dtotal / total - 1) > 1e-4) return 9;
+
+    // keep_going = false stops after the first full segment (raytracer.h:255-257)
+    std::atomic_bool stop{false};
+    int seen = 0;
+    auto partial = raytracer::run(dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{},
+                                  stop, [&](auto, auto) { ++seen; }, 4, 0.1f, 1000.0f, false, 0, 1);
+    if (partial.completed || seen != 1) return 10;
+    std::printf("RT_SHIM_OK energy=%g bins=%zu\n", total, res.histogram.histogram.size());
+    return 0;
+}

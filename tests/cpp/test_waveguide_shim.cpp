@@ -1,0 +1,62 @@
+// Mirrors src/waveguide/tests/waveguide_tests.cpp:43-139 (run_waveguide) against the
+// shim: a box mesh, soft source, four postprocessor::node receivers through the
+// generic callback path, the step-counter check (:105), and the same run through the
+// device-side stock path; prints the receiver traces for the python test to compare
+// with the oracle. Also checks the exception mapping of waveguide.h:100-119.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "wayverb_b200/waveguide.hpp"
+
+using namespace wayverb;
+using namespace wayverb::core;
+using namespace wayverb::waveguide;
+
+int main(int argc, char** argv) {
+    const int steps = argc > 1 ? atoi(argv[1]) : 60;
+    const compute_context cc{};
+    coefficients_canonical c{};
+    c.b[0] = argc > 2 ? strtod(argv[2], nullptr) : 39.0;  // impedance b0 of a flat surface
+    c.a[0] = 1.0;
+    auto m = make_cuboid_mesh(30, 24, 40, 0.1f, c);
+    const auto source_index = compute_index(m.get_descriptor(), 15, 12, 8);
+    if (!is_inside(m, source_index)) return 2;
+    std::vector<double> input(steps, 0.0);
+    input[0] = 1.0;
+    auto prep = preprocessor::make_soft_source(source_index, input.begin(), input.end());
+    std::vector<callback_accumulator<postprocessor::node>> holders;
+    for (int z : {12, 18, 24, 30}) holders.emplace_back(compute_index(m.get_descriptor(), 15, 12, z));
+    size_t callback_counter = 0;
+    bool counter_ok = true;
+    const auto done = run(
+            cc, m, [&](auto& queue, auto& buffer, auto step) { return prep(queue, buffer, step); },
+            [&](auto& queue, const auto& buffer, auto step) {
+                for (auto& i : holders) i(queue, buffer, step);
+                counter_ok = counter_ok && (step == callback_counter++);
+            },
+            true);
+    if (done != size_t(steps) || !counter_ok) return 3;
+
+    std::vector<double> out;
+    std::vector<size_t> rcv;
+    for (auto& h : holders) rcv.push_back(h.get_callback().get_output_node());
+    if (run_stock(cc, m, source_index, input, true, rcv, out) != size_t(steps)) return 4;
+    for (int s = 0; s < steps; ++s) {
+        for (size_t r = 0; r < holders.size(); ++r) {
+            const double a = holders[r].get_output()[s];
+            if (a != out[s * holders.size() + r]) return 5;  // callback path == device path
+            std::printf("%.17g%c", a, r + 1 == holders.size() ? '\n' : ' ');
+        }
+    }
+    std::vector<double> bad{std::nan("")};
+    try {
+        run(cc, m, preprocessor::make_hard_source(source_index, bad.begin(), bad.end()),
+            [](auto&, const auto&, auto) {}, true);
+        return 6;
+    } catch (const exceptions::value_is_nan&) {
+    }
+    return 0;
+}
