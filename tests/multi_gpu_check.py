@@ -34,11 +34,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    box = [wvb.waveguide.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
-    uid = box[0]
     ok = True
     for dims, kernel in (((140, 40, 12 * world + 5), _lib.KERNEL_TMA), ((37, 29, 8 * world + 3), _lib.KERNEL_DIRECT)):
+        # an ncclUniqueId serves exactly one communicator: a fresh one per handle
+        box = [wvb.waveguide.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
         dx, dy, dz = dims
         z0, z1 = wvb.slab_range(dz, rank, world)
         lo, hi = max(z0 - 1, 0), min(z1 + 1, dz)
