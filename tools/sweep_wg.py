@@ -34,7 +34,10 @@ def main():
     for st, mb, zc in ((4, 1, 12), (5, 1, 24), (5, 1, 37), (6, 1, 12), (5, 4, 24)):
         configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=st, WVB_WG_MINB=mb, WVB_WG_ZCHUNKS=zc,
                             WVB_WG_DIV=1, WVB_WG_OVERLAP=1))
-    for pf, zc in ((4, 64), (2, 32), (6, 32)):
+    for bm in (8, 5):
+        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
+                            WVB_WG_DIV=1, WVB_WG_OVERLAP=1, WVB_WG_BMINB=bm))
+    for pf, zc in ():
         configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=1, WVB_WG_PF=pf, WVB_WG_ZCHUNKS=zc, WVB_WG_OVERLAP=1))
     only = os.environ.get("SWEEP_ONLY")
     for cfg in configs:
