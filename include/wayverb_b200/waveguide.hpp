@@ -426,7 +426,58 @@ template <typename It>
 auto make_soft_source(size_t node, It begin, It end) {
     return soft_source<It>{node, begin, end};
 }
+/// gaussian.cpp:10-53: at step 0 the whole field is set to a 3-d gaussian centred
+/// on `centre_pos` (evaluated on the host in the reference's mixed float/double
+/// arithmetic, written as float values); the run lasts `steps` steps.
+class gaussian final {
+public:
+    static float compute(float dx, float dy, float dz, float sdev) {
+        const float len = std::sqrt(dx * dx + dy * dy + dz * dz);
+        return float(std::exp(-std::pow(double(len), 2) / (2 * std::pow(double(sdev), 2))) /
+                     std::pow(sdev * std::sqrt(2 * M_PI), 3));
+    }
+    gaussian(const mesh_descriptor& descriptor, float cx, float cy, float cz, float sdev, size_t steps)
+            : descriptor_(descriptor), cx_{cx}, cy_{cy}, cz_{cz}, sdev_{sdev}, steps_{steps} {}
+    bool operator()(cl::CommandQueue&, cl::Buffer& buffer, size_t step) const {
+        if (step == steps_) return false;
+        if (step == 0) {
+            const auto nodes = core::items_in_buffer<cl_double>(buffer);
+            util::aligned::vector<double> pressures;
+            pressures.reserve(nodes);
+            for (size_t i = 0; i != nodes; ++i) {
+                const auto l = compute_locator(descriptor_, i);
+                // compute_position (mesh_descriptor.cpp:27-34): min_corner + locator * spacing
+                const float px = descriptor_.min_corner.s[0] + float(l[0]) * descriptor_.spacing;
+                const float py = descriptor_.min_corner.s[1] + float(l[1]) * descriptor_.spacing;
+                const float pz = descriptor_.min_corner.s[2] + float(l[2]) * descriptor_.spacing;
+                pressures.emplace_back(compute(px - cx_, py - cy_, pz - cz_, sdev_));
+            }
+            core::detail::check(wvb_wg_write_field(buffer.handle(), pressures.data()));
+        }
+        return true;
+    }
+
+private:
+    mesh_descriptor descriptor_;
+    float cx_, cy_, cz_, sdev_;
+    size_t steps_;
+};
+
 }  // namespace preprocessor
+
+/// compute_neighbors (mesh_descriptor.cpp:36-57): nx, px, ny, py, nz, pz or no_neighbor
+inline std::array<cl_uint, 6> compute_neighbors(const mesh_descriptor& d, size_t index) {
+    const auto l = compute_locator(d, index);
+    const int dl[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    std::array<cl_uint, 6> ret;
+    for (int p = 0; p < 6; ++p) {
+        const int x = l[0] + dl[p][0], y = l[1] + dl[p][1], z = l[2] + dl[p][2];
+        const bool inside = 0 <= x && 0 <= y && 0 <= z && x < d.dimensions.s[0] &&
+                            y < d.dimensions.s[1] && z < d.dimensions.s[2];
+        ret[p] = inside ? cl_uint(compute_index(d, x, y, z)) : mesh_descriptor::no_neighbor;
+    }
+    return ret;
+}
 
 namespace postprocessor {
 /// node.cpp:14-18: the pressure at one node each step.
@@ -442,6 +493,61 @@ public:
 private:
     size_t output_node_;
 };
+/// directional_receiver.cpp:10-69: pressure + intensity (velocity from the pressure
+/// gradient of the six neighbours, integrated in double on the host). Reads are
+/// `cl_float` like the reference's, i.e. the fp64 device values are converted.
+class directional_receiver final {
+public:
+    directional_receiver(const mesh_descriptor& mesh_descriptor, double sample_rate,
+                         double ambient_density, size_t output_node)
+            : mesh_spacing_{mesh_descriptor.spacing}
+            , sample_rate_{sample_rate}
+            , ambient_density_{ambient_density}
+            , output_node_{output_node}
+            , surrounding_nodes_(compute_neighbors(mesh_descriptor, output_node)) {
+        for (const auto& i : surrounding_nodes_) {
+            if (i == ~cl_uint{0}) {
+                throw std::runtime_error(
+                        "Can't place directional_receiver at this node as it is adjacent to a "
+                        "boundary.");
+            }
+        }
+    }
+    struct output final {
+        float intensity[3];
+        float pressure;
+    };
+    using return_type = output;
+    return_type operator()(cl::CommandQueue& queue, const cl::Buffer& buffer, size_t) {
+        const auto pressure = core::read_value<cl_float>(queue, buffer, output_node_);
+        std::array<cl_float, 6> surrounding;
+        for (size_t i = 0; i != 6; ++i) {
+            surrounding[i] = cl_float(
+                    (core::read_value<cl_float>(queue, buffer, surrounding_nodes_[i]) - pressure) /
+                    mesh_spacing_);
+        }
+        const double m[3] = {(surrounding[1] - surrounding[0]) * 0.5,
+                             (surrounding[3] - surrounding[2]) * 0.5,
+                             (surrounding[5] - surrounding[4]) * 0.5};
+        output ret{};
+        for (int k = 0; k < 3; ++k) {
+            velocity_[k] -= m[k] / (ambient_density_ * sample_rate_);
+            ret.intensity[k] = float(velocity_[k] * double(pressure));
+        }
+        ret.pressure = pressure;
+        return ret;
+    }
+    size_t get_output_node() const { return output_node_; }
+
+private:
+    double mesh_spacing_;
+    double sample_rate_;
+    double ambient_density_;
+    size_t output_node_;
+    std::array<cl_uint, 6> surrounding_nodes_;
+    double velocity_[3]{0, 0, 0};
+};
+
 }  // namespace postprocessor
 
 }  // namespace waveguide

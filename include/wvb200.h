@@ -340,6 +340,14 @@ float wvb_rt_ray_energy(uint64_t total_rays, const float source[3], const float 
 uint32_t wvb_rt_safe_bins(const wvb_rt* rt, uint32_t depth, double speed_of_sound, double rate);
 
 /* ---- test hooks ------------------------------------------------------------- */
+/* The reference's device filter test kernels (cl/filters.cpp:56-75): n_streams
+ * parallel filters fed input[sample][stream] (float), output likewise.
+ * biquads != NULL: `filter_test`, three cascaded biquads per stream given as
+ * [stream][section][b0 b1 b2 a0 a1 a2]; else `filter_test_2` with one
+ * coefficients_canonical per stream. Filter memory starts at zero. */
+wvb_status wvb_test_filter(const double* biquads, const wvb_coefficients_canonical* canonical,
+                           const float* input, uint32_t n_streams, uint32_t n_samples, float* output);
+
 /* closest hit of n rays given as (position xyz, direction xyz); tri = ~0 for none.
  * Mirrors the comparison of src/raytracer/tests/reflector_tests.cpp:98-154. */
 wvb_status wvb_rt_closest_hit(wvb_rt* rt, const float* rays6, uint64_t n, uint32_t* tri_out,

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "wayverb_b200/waveguide.hpp"
@@ -15,8 +16,36 @@ using namespace wayverb;
 using namespace wayverb::core;
 using namespace wayverb::waveguide;
 
+// nan_in_waveguide.cpp:15-71 / canonical.h:65-81 style: gaussian excitation, directional
+// receiver; prints "pressure ix iy iz" per step
+static int gaussian_directional(int steps, double b0) {
+    const compute_context cc{};
+    coefficients_canonical c{};
+    c.b[0] = b0;
+    c.a[0] = 1.0;
+    auto m = make_cuboid_mesh(28, 26, 24, 0.05f, c);
+    const auto rcv = compute_index(m.get_descriptor(), 17, 12, 10);
+    callback_accumulator<postprocessor::directional_receiver> acc{m.get_descriptor(), 11776.0, 1.1765,
+                                                                   rcv};
+    const auto done = run(cc, m, preprocessor::gaussian{m.get_descriptor(), 0.6f, 0.65f, 0.55f, 0.1f, size_t(steps)},
+                          [&](auto& queue, const auto& buffer, auto step) { acc(queue, buffer, step); }, true);
+    if (done != size_t(steps)) return 7;
+    for (const auto& o : acc.get_output()) {
+        std::printf("%.9g %.9g %.9g %.9g\n", o.pressure, o.intensity[0], o.intensity[1], o.intensity[2]);
+    }
+    try {  // a receiver on the mesh edge has no six neighbours
+        postprocessor::directional_receiver bad{m.get_descriptor(), 1.0, 1.0, 0};
+        return 8;
+    } catch (const std::runtime_error&) {
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 60;
+    if (argc > 3 && std::string(argv[3]) == "gaussian") {
+        return gaussian_directional(steps, strtod(argv[2], nullptr));
+    }
     const compute_context cc{};
     coefficients_canonical c{};
     c.b[0] = argc > 2 ? strtod(argv[2], nullptr) : 39.0;  // impedance b0 of a flat surface

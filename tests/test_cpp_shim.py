@@ -48,6 +48,46 @@ def test_waveguide_run_template_matches_oracle(tmp_path):
 
 
 @pytest.mark.gpu
+def test_gaussian_preprocessor_and_directional_receiver(tmp_path):
+    """preprocessor::gaussian (gaussian.cpp:26-53) + postprocessor::directional_receiver
+    (directional_receiver.cpp:29-69) through the shim vs a numpy restatement on the
+    oracle's field."""
+    exe = build(tmp_path, "test_waveguide_shim")
+    steps = 40
+    c = wgo.to_flat(0.2)
+    r = subprocess.run([exe, str(steps), "%.17g" % c["b"][0], "gaussian"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+    dims, spacing = (28, 26, 24), np.float32(0.05)
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [c])
+    z, y, x = np.indices((dims[2], dims[1], dims[0]))
+    pos = [np.float32(0) + v.astype(np.float32) * spacing for v in (x, y, z)]
+    d = [pos[0] - np.float32(0.6), pos[1] - np.float32(0.65), pos[2] - np.float32(0.55)]
+    ln = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]).astype(np.float32)
+    sdev = np.float32(0.1)
+    g = (np.exp(-np.power(ln.astype(np.float64), 2) / (2 * np.power(np.float64(sdev), 2))) /
+         np.power(np.float64(sdev) * np.sqrt(2 * np.pi), 3)).astype(np.float32)
+    sim = wgo.Sim(om)
+    sim.set_field(g.astype(np.float64).ravel())
+    rcv = om.index(17, 12, 10)
+    nb = [om.index(16, 12, 10), om.index(18, 12, 10), om.index(17, 11, 10), om.index(17, 13, 10),
+          om.index(17, 12, 9), om.index(17, 12, 11)]
+    vel = np.zeros(3)
+    want = []
+    for _ in range(steps):
+        p = np.float32(sim.read(rcv))
+        s = [np.float32((np.float32(sim.read(n)) - p) / np.float64(spacing)) for n in nb]
+        m = np.array([(s[1] - s[0]) * 0.5, (s[3] - s[2]) * 0.5, (s[5] - s[4]) * 0.5], np.float64)
+        vel -= m / (1.1765 * 11776.0)
+        want.append([p] + [np.float32(v * np.float64(p)) for v in vel])
+        assert sim.step(1) == 0
+    want = np.array(want, np.float64)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
 def test_raytracer_run_template(tmp_path):
     exe = build(tmp_path, "test_raytracer_shim")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)

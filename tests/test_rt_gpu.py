@@ -128,8 +128,11 @@ def test_open_scene_dead_rays():
 
 def test_config5_sized_run_statistics():
     """1 M rays in a many-triangle room (config 5's ray count): energy bookkeeping must
-    agree with an independent 64 k-ray oracle run within the reference's statistical
-    criterion (10 % per band in the summed histogram, equal_energy.cpp:88)."""
+    agree with an independent 256 k-ray oracle run (different seed, different directions)
+    within the reference's statistical criterion (10 % per band, equal_energy.cpp:88).
+    The diffuse-rain part is compared on its own too: it is a sum over ~10^8 small
+    contributions and must agree much more tightly than the specular part, which is a
+    few thousand full-energy impulses."""
     sc = scene.box_scene((12.0, 8.0, 20.0), subdiv=12, side=16,
                          surfaces=[scene.make_surface([0.1, 0.1, 0.12, 0.15, 0.2, 0.25, 0.3, 0.35], 0.3)])
     src, rcv = [3.0, 2.0, 4.0], [8.0, 5.0, 15.0]
@@ -137,8 +140,13 @@ def test_config5_sized_run_statistics():
     with wvb.RayTracer(sc) as g:
         _, dropped, ms = g.trace(None, src, rcv, depth, n_rays=1 << 20, seed=9)
         big = g.histogram()
-    assert dropped == 0 and np.isfinite(big).all() and (big >= 0).all()
-    small, _, _ = rto.Scene(sc).trace(rto.directions(1234, 1 << 16), src, rcv, depth, seed=77)
-    per_band_big, per_band_small = big.sum(0), small.sum(0)
-    assert np.abs(per_band_big / per_band_small - 1).max() < 0.10
-    assert abs(big.sum() / small.sum() - 1) < 0.02
+        assert dropped == 0 and np.isfinite(big).all() and (big >= 0).all()
+        g.reset_histogram()
+        g.trace(None, src, rcv, depth, n_rays=1 << 20, seed=9, specular_from_step=depth)
+        big_diffuse = g.histogram()
+    o = rto.Scene(sc)
+    dirs = rto.directions(1234, 1 << 18)
+    small, _, _ = o.trace(dirs, src, rcv, depth, seed=77)
+    small_diffuse, _, _ = o.trace(dirs, src, rcv, depth, seed=77, specular_from_step=depth)
+    assert np.abs(big.sum(0) / small.sum(0) - 1).max() < 0.10
+    assert np.abs(big_diffuse.sum(0) / small_diffuse.sum(0) - 1).max() < 0.02

@@ -84,6 +84,37 @@ def test_division_by_three_is_correctly_rounded():
     assert ok_host.all()
 
 
+@pytest.mark.parametrize("kind", ["impulse", "noise", "quiet"])
+def test_device_filter_kernels(kind):
+    """tests/rectangular_kernel.cpp:242-360 on the device: `filter_test` (biquad cascade)
+    and `filter_test_2` (convolved canonical filter) on 256 parallel random peak-filter
+    sets: no NaN/Inf (also for +-1e-35 inputs), biquad == canonical within 1e-3, and both
+    identical to the oracle's restatement."""
+    rng = np.random.default_rng(17)
+    streams = 256
+    n = {"impulse": 200, "noise": 2000, "quiet": 4000}[kind]
+    biq = np.stack([[wgo.peak_biquad(rng.uniform(0.1, 1), rng.uniform(0, 0.5), rng.uniform(0, 1))
+                     for _ in range(3)] for _ in range(streams)])
+    canon = np.stack([wgo.convolve3(b) for b in biq]).view(_lib.COEFF_DT).reshape(streams)
+    if kind == "impulse":
+        x = np.zeros((n, streams), np.float32)
+        x[0] = 0.25
+    elif kind == "noise":
+        x = rng.uniform(-0.25, 0.25, (n, streams)).astype(np.float32)
+    else:
+        x = rng.uniform(-1e-35, 1e-35, (n, streams)).astype(np.float32)
+    y1, y2 = np.zeros_like(x), np.zeros_like(x)
+    bq = np.ascontiguousarray(biq, np.float64)
+    _lib.check(_lib.lib().wvb_test_filter(_lib.ptr(bq), None, _lib.ptr(x), streams, n, _lib.ptr(y1)))
+    _lib.check(_lib.lib().wvb_test_filter(None, _lib.ptr(canon), _lib.ptr(x), streams, n, _lib.ptr(y2)))
+    assert np.isfinite(y1).all() and np.isfinite(y2).all()
+    if kind != "quiet":
+        assert np.abs(y1 - y2).max() < 1e-3
+    for s in range(0, streams, 37):
+        assert np.array_equal(y1[:, s], wgo.filter_biquads(biq[s], x[:, s].copy()))
+        assert np.array_equal(y2[:, s], wgo.filter_canonical(canon[s], x[:, s].copy()))
+
+
 @pytest.mark.parametrize("kname,kernel", KERNELS)
 @pytest.mark.parametrize("dims", [(140, 24, 14), (150, 37, 19), (133, 11, 9), (260, 20, 12)])
 def test_box_plaster_field_and_filters(dims, kname, kernel):
@@ -239,6 +270,25 @@ def test_slab_handle_matches_whole_mesh_away_from_its_edges():
         want = o.field().reshape(dims[2], dims[1], dims[0])[6:14]
         got = g.field().reshape(8, dims[1], dims[0])
         assert np.array_equal(got[3:5], want[3:5])
+
+
+def test_config2_256_cube_rigid_against_oracle():
+    """BASELINE config 2 (256^3, rigid walls, hard source 1.0 at (128,128,128), receiver
+    (160,140,120)): the first 120 of its 10 000 steps against the oracle, full field and
+    receiver trace."""
+    dims = (256, 256, 256)
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [wgo.to_flat(0.0)])
+    src, rcv = om.index(128, 128, 128), [om.index(160, 140, 120)]
+    sig = np.zeros(120)
+    sig[0] = 1.0
+    o = wgo.Sim(om)
+    steps_o, out_o, flag_o = o.run(src, sig, rcv)
+    with wvb.Waveguide(to_wvb(om)) as g:
+        steps_g, out_g, flag_g = g.run_device(src, sig, rcv, check_interval=40)
+        assert (steps_o, flag_o) == (steps_g, flag_g) == (120, 0)
+        assert_parity(out_g, out_o, "receiver trace")
+        assert_parity(g.field(), o.field(), "field")
+        assert np.abs(out_o).max() > 0
 
 
 @pytest.mark.parametrize("dims,steps", [((256, 256, 64), 12)])

@@ -27,18 +27,11 @@ def main():
     m = wvb.cuboid_mesh(dims, [plaster()])
     nodes = dims[0] * dims[1] * dims[2]
     configs = []
-    for ov in (1, 0):
-        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
-                            WVB_WG_DIV=1, WVB_WG_OVERLAP=ov))
-        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=1, WVB_WG_PF=4, WVB_WG_ZCHUNKS=32, WVB_WG_OVERLAP=ov))
-    for st, mb, zc in ((4, 1, 12), (5, 1, 24), (5, 1, 37), (6, 1, 12), (5, 4, 24)):
-        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=st, WVB_WG_MINB=mb, WVB_WG_ZCHUNKS=zc,
-                            WVB_WG_DIV=1, WVB_WG_OVERLAP=1))
-    for bm in (8, 5):
-        configs.append(dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_STAGES=5, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12,
-                            WVB_WG_DIV=1, WVB_WG_OVERLAP=1, WVB_WG_BMINB=bm))
-    for pf, zc in ():
-        configs.append(dict(WVB_WG_KERNEL="direct", WVB_WG_DIV=1, WVB_WG_PF=pf, WVB_WG_ZCHUNKS=zc, WVB_WG_OVERLAP=1))
+    base = dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12, WVB_WG_DIV=1)
+    for st, pad, ov, bm in ((5, 0, 1, 5), (5, 0, 0, 5), (5, 28672, 1, 5), (5, 28672, 0, 5), (5, 28672, 1, 8),
+                            (7, 8192, 1, 5), (7, 8192, 0, 5), (8, 0, 1, 5), (8, 0, 0, 5), (6, 20480, 1, 5),
+                            (5, 57344, 1, 5), (8, 61440, 1, 5)):
+        configs.append(dict(base, WVB_WG_STAGES=st, WVB_WG_SMEM_PAD=pad, WVB_WG_OVERLAP=ov, WVB_WG_BMINB=bm))
     only = os.environ.get("SWEEP_ONLY")
     for cfg in configs:
         if only and cfg["WVB_WG_KERNEL"] != only:

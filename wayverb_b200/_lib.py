@@ -91,7 +91,7 @@ WG_SYMBOLS = [
     "wvb_wg_read_field_f32", "wvb_wg_write_field", "wvb_wg_step", "wvb_wg_launch", "wvb_wg_swap",
     "wvb_wg_run",
     "wvb_wg_boundary_count", "wvb_wg_read_boundary_data", "wvb_wg_time_steps", "wvb_wg_time_kernels",
-    "wvb_wg_get_info", "wvb_nccl_unique_id", "wvb_test_third",
+    "wvb_wg_get_info", "wvb_nccl_unique_id", "wvb_test_third", "wvb_test_filter",
     "wvb_mesh_cuboid", "wvb_version", "wvb_device_count", "wvb_last_error",
 ]
 
@@ -140,6 +140,7 @@ def lib():
     L.wvb_wg_time_steps.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(i32)]
     L.wvb_wg_time_kernels.argtypes = [vp, u32, C.POINTER(C.c_float * 2)]
     L.wvb_test_third.argtypes = [vp, C.c_size_t, vp, vp]
+    L.wvb_test_filter.argtypes = [vp, vp, vp, u32, u32, vp]
     L.wvb_nccl_unique_id.argtypes = [vp, C.c_size_t]
     L.wvb_wg_get_info.argtypes = [vp, C.POINTER(WgInfo)]
     L.wvb_mesh_cuboid.argtypes = [C.POINTER(i32 * 3), i32, i32, vp, C.POINTER(u64 * 3)]

@@ -94,7 +94,8 @@ struct wvb_wg {
     cudaStream_t stream_b = nullptr;  // boundary kernel runs here, next to the air kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
-    int bminb = 5;
+    int bminb = 8;
+    int smem_pad = 0;  // extra dynamic shared memory per air CTA: caps CTAs/SM, leaving room for boundary CTAs
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
     int ty = 8, nstage = 5, zchunks = 1;
@@ -210,15 +211,15 @@ inline int node_class(int32_t bt, int* ndims) {
 
 // ---- launch configuration ------------------------------------------------------
 template <class Cfg>
-void set_tma_attr() {
+void set_tma_attr(int pad) {
     WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)Cfg::SMEM_BYTES));
+                                  (int)Cfg::SMEM_BYTES + pad));
 }
 template <class Cfg>
-int tma_occupancy() {
+int tma_occupancy(int pad) {
     int nb = 0;
     WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg>, Cfg::THREADS,
-                                                           Cfg::SMEM_BYTES));
+                                                           Cfg::SMEM_BYTES + pad));
     return nb;
 }
 
@@ -261,7 +262,7 @@ void launch_tma(wvb_wg* w, const double* cur, double* prev) {
     const WgGeom& g = w->g;
     dim3 grid((g.dx + Cfg::TX - 1) / Cfg::TX, (g.dy + Cfg::TY - 1) / Cfg::TY, w->zchunks);
     (void)cur;  // read through the tensor map of P[w->cur]
-    wg_air_tma<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
+    wg_air_tma<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES + w->smem_pad, w->stream>>>(
             w->map[w->cur], prev, w->code.p, g, w->zchunks, w->flag.p);
 }
 
@@ -273,6 +274,8 @@ void launch_tma(wvb_wg* w, const double* cur, double* prev) {
     X(8, 4, true, 1)       \
     X(8, 4, true, 4)       \
     X(8, 6, true, 1)       \
+    X(8, 7, true, 1)       \
+    X(8, 8, true, 1)       \
     X(16, 5, true, 1)
 
 template <class F>
@@ -554,7 +557,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
-    w->bminb = env_int("WVB_WG_BMINB", 5);
+    w->bminb = env_int("WVB_WG_BMINB", 8);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);
@@ -585,21 +588,22 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->fast_div = env_int("WVB_WG_DIV", 1) ? 1 : 0;
     w->pf = env_int("WVB_WG_PF", 4);
     w->minb = env_int("WVB_WG_MINB", 1);
+    w->smem_pad = env_int("WVB_WG_SMEM_PAD", 0) & ~127;
     int slots;
     long long tiles;
     if (w->variant == WVB_WG_KERNEL_TMA) {
         int occ = 0;
         const bool known = with_tma_cfg(w, [&](auto cfg) {
             using Cfg = decltype(cfg);
-            set_tma_attr<Cfg>();
-            occ = tma_occupancy<Cfg>();
+            set_tma_attr<Cfg>(w->smem_pad);
+            occ = tma_occupancy<Cfg>(w->smem_pad);
         });
         if (!known) {  // unknown combination: fall back to the default configuration
             w->ty = 8; w->nstage = 5; w->fast_div = 1; w->minb = 1;
             with_tma_cfg(w, [&](auto cfg) {
                 using Cfg = decltype(cfg);
-                set_tma_attr<Cfg>();
-                occ = tma_occupancy<Cfg>();
+                set_tma_attr<Cfg>(w->smem_pad);
+                occ = tma_occupancy<Cfg>(w->smem_pad);
             });
         }
         make_tensor_map(w, 0, w->ty);
@@ -850,6 +854,24 @@ wvb_status wvb_test_third(const double* in, size_t n, double* fast, double* ref)
         WVB_CUDA(cudaGetLastError());
         WVB_CUDA(cudaMemcpy(fast, b.p, n * 8, cudaMemcpyDeviceToHost));
         WVB_CUDA(cudaMemcpy(ref, c.p, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+wvb_status wvb_test_filter(const double* biquads, const wvb_coefficients_canonical* canonical,
+                           const float* input, uint32_t n_streams, uint32_t n_samples, float* output) {
+    if ((!biquads && !canonical) || !input || !output) return WVB_ERR_INVALID;
+    return guarded([&] {
+        dev_buf<double> d_bq;
+        dev_buf<wvb_coefficients_canonical> d_c;
+        dev_buf<float> d_in, d_out;
+        if (biquads) d_bq.upload(biquads, (size_t)n_streams * 18);
+        else d_c.upload(canonical, n_streams);
+        d_in.upload(input, (size_t)n_streams * n_samples);
+        d_out.alloc((size_t)n_streams * n_samples, false);
+        wg_filter_test<<<(n_streams + 63) / 64, 64>>>(biquads ? d_bq.p : nullptr, d_c.p, d_in.p, d_out.p,
+                                                      n_streams, n_samples);
+        WVB_CUDA(cudaGetLastError());
+        WVB_CUDA(cudaMemcpy(output, d_out.p, (size_t)n_streams * n_samples * 4, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -565,6 +565,51 @@ __device__ __forceinline__ int boundary_node(const double* __restrict__ cur,
     return bad;
 }
 
+// filter_step_biquad (cl/filters.cpp:17-36 with order 2) and biquad_cascade (:44-54)
+__device__ __forceinline__ double filter_step_2(double input, double* m, const double* b,
+                                                const double* a) {
+    const double output = (input * b[0] + m[0]) / a[0];
+    const double b1 = b[1] == 0 ? 0 : b[1] * input;
+    const double a1 = a[1] == 0 ? 0 : a[1] * output;
+    m[0] = b1 - a1 + m[1];
+    const double b2 = b[2] == 0 ? 0 : b[2] * input;
+    const double a2 = a[2] == 0 ? 0 : a[2] * output;
+    m[1] = b2 - a2;
+    return output;
+}
+// Test kernels of the device filter step: `filter_test` (biquad cascade) and
+// `filter_test_2` (canonical 6th order), cl/filters.cpp:56-75. One thread per
+// stream; input[sample][stream] float, output float, as in the reference; the
+// per-sample launches of tests/rectangular_kernel.cpp:180-200 become a loop with
+// the filter memory in registers.
+__global__ void wg_filter_test(const double* __restrict__ biquads /* [stream][3][b3,a3] or null */,
+                               const wvb_coefficients_canonical* __restrict__ canon,
+                               const float* __restrict__ input, float* __restrict__ output,
+                               uint32_t n_streams, uint32_t n_samples) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    if (biquads) {
+        double bq[18], mem[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 18; ++i) bq[i] = biquads[(size_t)s * 18 + i];
+        for (uint32_t k = 0; k < n_samples; ++k) {
+            double x = input[(size_t)k * n_streams + s];
+            for (int sec = 0; sec < 3; ++sec) {
+                x = filter_step_2(x, mem + 2 * sec, bq + 6 * sec, bq + 6 * sec + 3);
+            }
+            output[(size_t)k * n_streams + s] = (float)x;
+        }
+    } else {
+        const wvb_coefficients_canonical c = canon[s];
+        double mem[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t k = 0; k < n_samples; ++k) {
+            const double in = input[(size_t)k * n_streams + s];
+            const double out = (in * c.b[0] + mem[0]) / c.a[0];  // output of filter_step_6
+            filter_step_6(in, mem, c);
+            output[(size_t)k * n_streams + s] = (float)out;
+        }
+    }
+}
+
 // All three boundary classes in one launch: blocks [0, nb1) walk the 1-d list,
 // [nb1, nb1 + nb2) the 2-d list, the rest the 3-d list. Runs on its own stream
 // next to the air-node kernel: the two touch disjoint nodes of `prev` and only
