@@ -148,7 +148,8 @@ void wvb_wg_destroy(wvb_wg* wg);
  * `node` = global node index. Writes go to every local copy (owned plane or
  * ghost plane) so all ranks may issue the same write. *owned (optional) tells
  * whether this handle owns the node; a read of a node that is neither owned
- * nor in a ghost plane returns 0.0 with *owned = 0. Both synchronise. */
+ * nor in a ghost plane returns 0.0 with *owned = 0. The read synchronises; the
+ * write is ordered on the handle's stream ahead of every later call. */
 wvb_status wvb_wg_write_f64(wvb_wg* wg, uint64_t node, double value);
 wvb_status wvb_wg_read_f64(wvb_wg* wg, uint64_t node, double* value, int* owned);
 

@@ -170,8 +170,14 @@ __device__ __forceinline__ float tri_intersection(const TriPre& T, f3 pos, f3 di
 
 // VOXEL_TRAVERSAL_ALGORITHM + voxel_traversal + ray_triangle_group_intersection
 // (voxel.cpp:22-95, geometry.cpp:103-148). Returns t (0 = none) and the index.
+// t_stop: the walk ends (returning "no hit") before visiting a voxel whose entry
+// distance already exceeds t_stop. With INFINITY this is the reference's walk.
+// The visibility query passes the distance to the receiver: a hit accepted in a
+// voxel entered at e > t_stop has t >= e > t_stop (voxel lists are conservative
+// supersets of the triangles touching the voxel, so a nearer hit would have been
+// accepted in the voxel that contains it), and `!t || mag < t` is true either way.
 __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir, uint32_t avoid,
-                                                 uint32_t& index) {
+                                                 uint32_t& index, float t_stop = INFINITY) {
     index = 0;
     const float sidef = (float)sc.side;
     const f3 vd = mk((sc.c1.x - sc.c0.x) / sidef, (sc.c1.y - sc.c0.y) / sidef,
@@ -218,6 +224,7 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
             index = best_i;
             return best_t;
         }
+        if (tmin > t_stop) break;  // the next voxel starts beyond the point of interest
         if (min_i == 0) {
             ix += stx;
             if (ix == jox) break;
@@ -241,7 +248,7 @@ __device__ __forceinline__ bool point_visible(const Scene& sc, f3 begin, f3 poin
     const float mag = length(b2p);
     const f3 direction = normalize(b2p);
     uint32_t idx;
-    const float t = voxel_traversal(sc, begin, direction, avoid, idx);
+    const float t = voxel_traversal(sc, begin, direction, avoid, idx, mag);
     return !t || mag < t;
 }
 

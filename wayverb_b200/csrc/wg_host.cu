@@ -681,9 +681,11 @@ wvb_status wvb_wg_write_f64(wvb_wg* w, uint64_t node, double value) {
         WVB_CUDA(cudaSetDevice(w->dev));
         const long long off = local_offset(w, node, nullptr);
         if (off < 0) return;
+        // pageable source: the runtime stages the 8 bytes before returning, and every
+        // later operation of this handle is ordered behind the copy on the same stream,
+        // so no host synchronisation is needed here
         WVB_CUDA(cudaMemcpyAsync(w->P[w->cur].p + off, &value, sizeof(double),
                                  cudaMemcpyHostToDevice, w->stream));
-        WVB_CUDA(cudaStreamSynchronize(w->stream));
     });
 }
 
