@@ -27,11 +27,10 @@ def main():
     m = wvb.cuboid_mesh(dims, [plaster()])
     nodes = dims[0] * dims[1] * dims[2]
     configs = []
-    base = dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12, WVB_WG_DIV=1)
-    for st, pad, ov, bm in ((5, 0, 1, 5), (5, 0, 0, 5), (5, 28672, 1, 5), (5, 28672, 0, 5), (5, 28672, 1, 8),
-                            (7, 8192, 1, 5), (7, 8192, 0, 5), (8, 0, 1, 5), (8, 0, 0, 5), (6, 20480, 1, 5),
-                            (5, 57344, 1, 5), (8, 61440, 1, 5)):
-        configs.append(dict(base, WVB_WG_STAGES=st, WVB_WG_SMEM_PAD=pad, WVB_WG_OVERLAP=ov, WVB_WG_BMINB=bm))
+    base = dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_MINB=1, WVB_WG_ZCHUNKS=12, WVB_WG_DIV=1, WVB_WG_STAGES=5)
+    for bt, bm, af, ov in ((128, 8, 0, 1), (128, 8, 1, 1), (64, 16, 1, 1), (64, 16, 0, 1), (64, 10, 1, 1),
+                           (32, 32, 1, 1), (64, 16, 0, 0), (128, 8, 0, 0)):
+        configs.append(dict(base, WVB_WG_BTHREADS=bt, WVB_WG_BMINB=bm, WVB_WG_AIRFIRST=af, WVB_WG_OVERLAP=ov))
     only = os.environ.get("SWEEP_ONLY")
     for cfg in configs:
         if only and cfg["WVB_WG_KERNEL"] != only:

@@ -199,19 +199,36 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
     if (isnan(tmy)) tmy = INFINITY;
     if (isnan(tmz)) tmz = INFINITY;
     const float tdx = fabsf(vd.x / dir.x), tdy = fabsf(vd.y / dir.y), tdz = fabsf(vd.z / dir.z);
+    // The reference nests "for each voxel { for each triangle }". On a SIMT machine
+    // that nest leaves most lanes idle (ncu: 3.8 of 32 threads active per issued
+    // instruction) because lanes reach their few non-empty voxels at different
+    // times. The same walk is therefore run as a flat state machine: every
+    // iteration a lane either enters a voxel, tests ONE triangle of the current
+    // voxel, or leaves the voxel -- identical visiting and testing order, identical
+    // arithmetic, identical result.
+    uint32_t i = 0, num = 0;
+    const uint32_t* begin = sc.voxel_index;
+    float best_t = 0.0f, tmin = 0.0f;
+    uint32_t best_i = 0;
+    int min_i = 0;
+    bool enter = true;
     for (;;) {
-        int min_i = 0;
-        float tmin = tmx;
-        if (tmy < tmin) { min_i = 1; tmin = tmy; }
-        if (tmz < tmin) { min_i = 2; tmin = tmz; }
-        const uint32_t voxel_offset =
-                sc.voxel_index[(size_t)ix * side * side + (size_t)iy * side + iz];
-        const uint32_t num = sc.voxel_index[voxel_offset];
-        const uint32_t* begin = sc.voxel_index + voxel_offset + 1;
-        float best_t = 0.0f;
-        uint32_t best_i = 0;
-        for (uint32_t i = 0; i != num; ++i) {
+        if (enter) {
+            min_i = 0;
+            tmin = tmx;
+            if (tmy < tmin) { min_i = 1; tmin = tmy; }
+            if (tmz < tmin) { min_i = 2; tmin = tmz; }
+            const uint32_t voxel_offset =
+                    sc.voxel_index[(size_t)ix * side * side + (size_t)iy * side + iz];
+            num = sc.voxel_index[voxel_offset];
+            begin = sc.voxel_index + voxel_offset + 1;
+            i = 0;
+            best_t = 0.0f;
+            enter = false;
+        }
+        if (i < num) {
             const uint32_t ti = begin[i];
+            ++i;
             if (ti != avoid) {
                 const float t = tri_intersection(sc.pre[ti], pos, dir);
                 if (t && (!best_t || t < best_t)) {
@@ -220,23 +237,26 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
                 }
             }
         }
-        if (best_t && best_t <= tmin) {
-            index = best_i;
-            return best_t;
-        }
-        if (tmin > t_stop) break;  // the next voxel starts beyond the point of interest
-        if (min_i == 0) {
-            ix += stx;
-            if (ix == jox) break;
-            tmx += tdx;
-        } else if (min_i == 1) {
-            iy += sty;
-            if (iy == joy) break;
-            tmy += tdy;
-        } else {
-            iz += stz;
-            if (iz == joz) break;
-            tmz += tdz;
+        if (i >= num) {
+            if (best_t && best_t <= tmin) {
+                index = best_i;
+                return best_t;
+            }
+            if (tmin > t_stop) break;  // the next voxel starts beyond the point of interest
+            if (min_i == 0) {
+                ix += stx;
+                if (ix == jox) break;
+                tmx += tdx;
+            } else if (min_i == 1) {
+                iy += sty;
+                if (iy == joy) break;
+                tmy += tdy;
+            } else {
+                iz += stz;
+                if (iz == joz) break;
+                tmz += tdz;
+            }
+            enter = true;
         }
     }
     return 0.0f;

@@ -95,6 +95,8 @@ struct wvb_wg {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
     int bminb = 8;
+    int bthreads = 128;
+    int air_first = 0;
     int smem_pad = 0;  // extra dynamic shared memory per air CTA: caps CTAs/SM, leaving room for boundary CTAs
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
@@ -314,23 +316,30 @@ void launch_air(wvb_wg* w, const double* cur, double* prev) {
     w->launches++;
 }
 
-void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
+template <int THREADS, int MINB>
+void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     const uint32_t n1 = w->bl[0].n, n2 = w->bl[1].n, n3 = w->bl[2].n;
-    if (!(n1 + n2 + n3)) return;
-    const uint32_t T = WG_BND_THREADS;
+    const uint32_t T = THREADS;
     const uint32_t nb1 = (n1 + T - 1) / T, nb2 = (n2 + T - 1) / T, nb3 = (n3 + T - 1) / T;
     auto L = [&](int k) {
         auto& l = w->bl[k];
         return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
     };
-    if (w->bminb >= 8) {
-        wg_boundary_all<8><<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
-                                                          w->coeffs.p, w->g, w->courant,
-                                                          w->courant_sq, w->flag.p);
+    wg_boundary_all<THREADS, MINB><<<nb1 + nb2 + nb3, T, 0, st>>>(
+            cur, prev, L(0), L(1), L(2), nb1, nb2, w->coeffs.p, w->g, w->courant, w->courant_sq,
+            w->flag.p);
+}
+
+void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
+    if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
+    if (w->bthreads == 64) {
+        if (w->bminb >= 16) launch_boundary_t<64, 16>(w, cur, prev, st);
+        else launch_boundary_t<64, 10>(w, cur, prev, st);
+    } else if (w->bthreads == 32) {
+        launch_boundary_t<32, 32>(w, cur, prev, st);
     } else {
-        wg_boundary_all<5><<<nb1 + nb2 + nb3, T, 0, st>>>(cur, prev, L(0), L(1), L(2), nb1, nb2,
-                                                          w->coeffs.p, w->g, w->courant,
-                                                          w->courant_sq, w->flag.p);
+        if (w->bminb >= 8) launch_boundary_t<128, 8>(w, cur, prev, st);
+        else launch_boundary_t<128, 5>(w, cur, prev, st);
     }
     w->launches++;
 }
@@ -370,12 +379,17 @@ void enqueue_launch(wvb_wg* w) {
     const bool has_boundary = w->bl[0].n + w->bl[1].n + w->bl[2].n;
     if (w->overlap && has_boundary) {
         // the boundary lists and the air kernel write disjoint nodes of `prev`:
-        // fork the boundary launch onto its own (higher priority) stream
+        // fork the boundary launch onto its own stream
         WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
         WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
-        launch_boundary(w, cur, prev, w->stream_b);
+        if (w->air_first) {
+            launch_air(w, cur, prev);
+            launch_boundary(w, cur, prev, w->stream_b);
+        } else {
+            launch_boundary(w, cur, prev, w->stream_b);
+            launch_air(w, cur, prev);
+        }
         WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
-        launch_air(w, cur, prev);
         WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
     } else {
         launch_air(w, cur, prev);
@@ -550,14 +564,17 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     // ---- device state ------------------------------------------------------------
     int prio_lo = 0, prio_hi = 0;
     WVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, prio_lo));
-    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_b, cudaStreamNonBlocking, prio_hi));
+    const int air_first = env_int("WVB_WG_AIRFIRST", 0);
+    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, air_first ? prio_hi : prio_lo));
+    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_b, cudaStreamNonBlocking, air_first ? prio_lo : prio_hi));
     WVB_CUDA(cudaEventCreate(&w->ev0));
     WVB_CUDA(cudaEventCreate(&w->ev1));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 8);
+    w->bthreads = env_int("WVB_WG_BTHREADS", 128);
+    w->air_first = env_int("WVB_WG_AIRFIRST", 0);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);

@@ -614,9 +614,8 @@ __global__ void wg_filter_test(const double* __restrict__ biquads /* [stream][3]
 // [nb1, nb1 + nb2) the 2-d list, the rest the 3-d list. Runs on its own stream
 // next to the air-node kernel: the two touch disjoint nodes of `prev` and only
 // read `cur`.
-constexpr int WG_BND_THREADS = 128;
-template <int MINB>
-__global__ void __launch_bounds__(WG_BND_THREADS, MINB)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
                 BList L3, uint32_t nb1, uint32_t nb2,
                 const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g, double courant,
@@ -624,13 +623,13 @@ wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList
     int bad = 0;
     const uint32_t b = blockIdx.x;
     if (b < nb1) {
-        const uint32_t t = b * WG_BND_THREADS + threadIdx.x;
+        const uint32_t t = b * THREADS + threadIdx.x;
         if (t < L1.n) bad = boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
     } else if (b < nb1 + nb2) {
-        const uint32_t t = (b - nb1) * WG_BND_THREADS + threadIdx.x;
+        const uint32_t t = (b - nb1) * THREADS + threadIdx.x;
         if (t < L2.n) bad = boundary_node<2>(cur, prev, L2, t, coeffs, g, courant, courant_sq);
     } else {
-        const uint32_t t = (b - nb1 - nb2) * WG_BND_THREADS + threadIdx.x;
+        const uint32_t t = (b - nb1 - nb2) * THREADS + threadIdx.x;
         if (t < L3.n) bad = boundary_node<3>(cur, prev, L3, t, coeffs, g, courant, courant_sq);
     }
     raise_flags(bad, flag);
