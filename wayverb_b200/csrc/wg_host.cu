@@ -97,6 +97,9 @@ struct wvb_wg {
     int bminb = 8;
     int bthreads = 128;
     int air_first = 0;
+    int persist = 0;
+    int air_slots = 0;
+    dev_buf<unsigned> work_counter;
     int smem_pad = 0;  // extra dynamic shared memory per air CTA: caps CTAs/SM, leaving room for boundary CTAs
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
@@ -214,14 +217,21 @@ inline int node_class(int32_t bt, int* ndims) {
 // ---- launch configuration ------------------------------------------------------
 template <class Cfg>
 void set_tma_attr(int pad) {
-    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES + pad));
+    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::SMEM_BYTES + pad));
 }
 template <class Cfg>
-int tma_occupancy(int pad) {
+int tma_occupancy(int pad, bool persist) {
     int nb = 0;
-    WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg>, Cfg::THREADS,
-                                                           Cfg::SMEM_BYTES + pad));
+    if (persist) {
+        WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg, true>, Cfg::THREADS,
+                                                               Cfg::SMEM_BYTES + pad));
+    } else {
+        WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg, false>, Cfg::THREADS,
+                                                               Cfg::SMEM_BYTES + pad));
+    }
     return nb;
 }
 
@@ -262,10 +272,21 @@ void make_tensor_map(wvb_wg* w, int which, int ty) {
 template <class Cfg>
 void launch_tma(wvb_wg* w, const double* cur, double* prev) {
     const WgGeom& g = w->g;
-    dim3 grid((g.dx + Cfg::TX - 1) / Cfg::TX, (g.dy + Cfg::TY - 1) / Cfg::TY, w->zchunks);
     (void)cur;  // read through the tensor map of P[w->cur]
-    wg_air_tma<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES + w->smem_pad, w->stream>>>(
-            w->map[w->cur], prev, w->code.p, g, w->zchunks, w->flag.p);
+    const int tiles_x = (g.dx + Cfg::TX - 1) / Cfg::TX, tiles_y = (g.dy + Cfg::TY - 1) / Cfg::TY;
+    const unsigned items = (unsigned)tiles_x * tiles_y * w->zchunks;
+    const size_t smem = Cfg::SMEM_BYTES + w->smem_pad;
+    if (w->persist) {
+        WVB_CUDA(cudaMemsetAsync(w->work_counter.p, 0, sizeof(unsigned), w->stream));
+        const unsigned grid = std::min<unsigned>(items, (unsigned)w->air_slots);
+        wg_air_tma<Cfg, true><<<grid, Cfg::THREADS, smem, w->stream>>>(
+                w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->work_counter.p,
+                w->flag.p);
+    } else {
+        wg_air_tma<Cfg, false><<<items, Cfg::THREADS, smem, w->stream>>>(
+                w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->work_counter.p,
+                w->flag.p);
+    }
 }
 
 // the TMA configurations that are compiled in: (TY, stages, fast division, min CTAs/SM)
@@ -606,6 +627,8 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->pf = env_int("WVB_WG_PF", 4);
     w->minb = env_int("WVB_WG_MINB", 1);
     w->smem_pad = env_int("WVB_WG_SMEM_PAD", 0) & ~127;
+    w->persist = env_int("WVB_WG_PERSIST", 0);
+    w->work_counter.alloc(1, true, &w->device_bytes);
     int slots;
     long long tiles;
     if (w->variant == WVB_WG_KERNEL_TMA) {
@@ -613,19 +636,20 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         const bool known = with_tma_cfg(w, [&](auto cfg) {
             using Cfg = decltype(cfg);
             set_tma_attr<Cfg>(w->smem_pad);
-            occ = tma_occupancy<Cfg>(w->smem_pad);
+            occ = tma_occupancy<Cfg>(w->smem_pad, w->persist != 0);
         });
         if (!known) {  // unknown combination: fall back to the default configuration
             w->ty = 8; w->nstage = 5; w->fast_div = 1; w->minb = 1;
             with_tma_cfg(w, [&](auto cfg) {
                 using Cfg = decltype(cfg);
                 set_tma_attr<Cfg>(w->smem_pad);
-                occ = tma_occupancy<Cfg>(w->smem_pad);
+                occ = tma_occupancy<Cfg>(w->smem_pad, w->persist != 0);
             });
         }
         make_tensor_map(w, 0, w->ty);
         make_tensor_map(w, 1, w->ty);
         slots = std::max(1, occ) * w->sm_count;
+        w->air_slots = slots;
         tiles = (long long)((dx + 127) / 128) * ((dy + w->ty - 1) / w->ty);
     } else {
         slots = 4 * w->sm_count;

@@ -307,24 +307,26 @@ struct TmaCfg {
     static_assert(NSTAGE >= 4, "need 3 live planes + at least one in flight");
 };
 
-template <class Cfg>
+// Work item = (x tile, y tile, z chunk), numbered x fastest. PERSIST = false:
+// one item per CTA (grid = number of items). PERSIST = true: the grid is the
+// number of CTAs that fit on the chip and every CTA pulls items from a global
+// counter until none are left; all CTAs are then resident from the start, which
+// lets the (register-light) boundary kernel on the second stream occupy the
+// resources they leave over, instead of queueing behind ~3000 waiting CTAs.
+template <class Cfg, bool PERSIST>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ prev,
-           const uint8_t* __restrict__ code, WgGeom g, int zchunks, int* __restrict__ flag) {
+           const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y, int zchunks,
+           unsigned int* __restrict__ work_counter, int* __restrict__ flag) {
     constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
     constexpr int R = Cfg::ROWS_PER_THREAD;
     extern __shared__ unsigned char smem_raw[];
+    __shared__ unsigned int s_item;
     // 128-byte aligned stage ring followed by the mbarriers (shared-window addresses)
     const uint32_t base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t bars = base + NS * Cfg::STAGE_BYTES;
-
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX;
-    const int y0 = blockIdx.y * TY;
-    // z range of this CTA: owned local planes [zs, ze)
-    const int zs = 1 + (int)(((long long)g.nzl * blockIdx.z) / zchunks);
-    const int ze = 1 + (int)(((long long)g.nzl * (blockIdx.z + 1)) / zchunks);
-    const int n_planes = ze - zs + 2;  // planes zs-1 .. ze are streamed
+    const unsigned n_items = (unsigned)tiles_x * tiles_y * zchunks;
 
     if (tid == 0) {
         tma::prefetch_map(&cur_map);
@@ -332,111 +334,137 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
         tma::fence_barrier_init();
         tma::fence_proxy_async();
     }
-    __syncthreads();
-
-    // box origin in the padded array: column WG_XO + x0 - HX, row (y0 - 1) + 1
-    const int bx = WG_XO + x0 - Cfg::HX, by = y0;
-    int issued = 0;  // planes requested so far (meaningful in thread 0 only)
-    if (tid == 0) {
-        const int pre = n_planes < NS ? n_planes : NS;
-        for (; issued < pre; ++issued) {
-            tma::mbar_arrive_expect_tx(bars + 8 * issued, Cfg::BOX_BYTES);
-            tma::load_box_3d(base + issued * Cfg::STAGE_BYTES, &cur_map, bars + 8 * issued, bx, by,
-                             zs - 1 + issued);
-        }
-    }
-
     // thread -> nodes: pair column tx (x = x0 + 2 tx), rows ty + 4 rr
     const int tx = tid & 63;
     const int ty = tid >> 6;
-    const int x = x0 + 2 * tx;
-    bool valid[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) valid[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
     const uint32_t sp = (uint32_t)g.plane, ksp = (uint32_t)g.cplane;
-    uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, zs);  // row rr: + 4 rr px
-    uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + x);
     const uint32_t rstep = 4u * (uint32_t)g.px, krstep = 4u * (uint32_t)g.pc;
     // byte offset of this thread's centre pair inside a stage (row rr: + 4 rr BOXX 8)
     const uint32_t so = (uint32_t)(((ty + 1) * BOXX + 2 * tx + Cfg::HX) * 8);
 
-    double2 p_next[R];
-    unsigned c_next[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-        p_next[rr] = make_double2(0.0, 0.0);
-        c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 8);
-        if (valid[rr]) {
-            p_next[rr] = ld2(prev + (off + rr * rstep));
-            c_next[rr] = *reinterpret_cast<const unsigned short*>(code + (koff + rr * krstep));
-        }
-    }
-
-    // ring state: stage of plane z-1, stage + phase bit of plane z+1
-    int st_b = 0;
-    int st_a = 2;
-    uint32_t ph_a = 0;
-    tma::mbar_wait(bars + 0, 0);
-    tma::mbar_wait(bars + 8, 0);
-
+    // planes are numbered consecutively over the whole life of the CTA: plane number
+    // s lives in stage s % NS and completes phase (s / NS) & 1 of that stage's barrier
+    unsigned seq = 0;
     int bad = 0;
-    for (int z = zs; z < ze; ++z) {
-        tma::mbar_wait(bars + 8 * st_a, ph_a);
-        int st_m = st_b + 1;
-        if (st_m == NS) st_m = 0;
-        const uint32_t sb = base + st_b * Cfg::STAGE_BYTES + so;
-        const uint32_t sm = base + st_m * Cfg::STAGE_BYTES + so;
-        const uint32_t sa = base + st_a * Cfg::STAGE_BYTES + so;
+    unsigned item = PERSIST ? 0u : blockIdx.x;
+    for (;;) {
+        if (PERSIST) {
+            if (tid == 0) s_item = atomicAdd(work_counter, 1u);
+            __syncthreads();  // publishes s_item; also: every thread is done with all stages
+            item = s_item;
+            if (item >= n_items) break;
+        } else {
+            __syncthreads();  // barrier init visible
+        }
+        const int tile_x = (int)(item % (unsigned)tiles_x);
+        const int tile_y = (int)((item / (unsigned)tiles_x) % (unsigned)tiles_y);
+        const int chunk = (int)(item / ((unsigned)tiles_x * (unsigned)tiles_y));
+        const int x0 = tile_x * TX;
+        const int y0 = tile_y * TY;
+        // z range of this item: owned local planes [zs, ze); planes zs-1 .. ze are streamed
+        const int zs = 1 + (int)(((long long)g.nzl * chunk) / zchunks);
+        const int ze = 1 + (int)(((long long)g.nzl * (chunk + 1)) / zchunks);
+        const int n_planes = ze - zs + 2;
+        // box origin in the padded array: column WG_XO + x0 - HX, row (y0 - 1) + 1
+        const int bx = WG_XO + x0 - Cfg::HX, by = y0;
 
-        double2 p[R];
-        unsigned c[R];
+        int issued = 0;  // planes of this item requested so far (meaningful in thread 0 only)
+        if (tid == 0) {
+            const int pre = n_planes < NS ? n_planes : NS;
+            for (; issued < pre; ++issued) {
+                const unsigned st = (seq + issued) % NS;
+                tma::mbar_arrive_expect_tx(bars + 8 * st, Cfg::BOX_BYTES);
+                tma::load_box_3d(base + st * Cfg::STAGE_BYTES, &cur_map, bars + 8 * st, bx, by,
+                                 zs - 1 + issued);
+            }
+        }
+
+        const int x = x0 + 2 * tx;
+        bool valid[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) valid[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
+        uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, zs);  // row rr: + 4 rr px
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + x);
+
+        double2 p_next[R];
+        unsigned c_next[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
-            p[rr] = p_next[rr];
-            c[rr] = c_next[rr];
+            p_next[rr] = make_double2(0.0, 0.0);
+            c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 8);
+            if (valid[rr]) {
+                p_next[rr] = ld2(prev + (off + rr * rstep));
+                c_next[rr] = *reinterpret_cast<const unsigned short*>(code + (koff + rr * krstep));
+            }
         }
-        if (z + 1 < ze) {
+
+        // ring state: stage of plane z-1, stage + phase bit of plane z+1
+        int st_b = (int)(seq % NS);
+        int st_a = (int)((seq + 2) % NS);
+        uint32_t ph_a = ((seq + 2) / NS) & 1u;
+        tma::mbar_wait(bars + 8 * st_b, (seq / NS) & 1u);
+        tma::mbar_wait(bars + 8 * ((seq + 1) % NS), ((seq + 1) / NS) & 1u);
+
+        for (int z = zs; z < ze; ++z) {
+            tma::mbar_wait(bars + 8 * st_a, ph_a);
+            int st_m = st_b + 1;
+            if (st_m == NS) st_m = 0;
+            const uint32_t sb = base + st_b * Cfg::STAGE_BYTES + so;
+            const uint32_t sm = base + st_m * Cfg::STAGE_BYTES + so;
+            const uint32_t sa = base + st_a * Cfg::STAGE_BYTES + so;
+
+            double2 p[R];
+            unsigned c[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                p[rr] = p_next[rr];
+                c[rr] = c_next[rr];
+            }
+            if (z + 1 < ze) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    if (valid[rr]) {
+                        p_next[rr] = ld2(prev + (off + sp + rr * rstep));
+                        c_next[rr] = *reinterpret_cast<const unsigned short*>(
+                                code + (koff + ksp + rr * krstep));
+                    }
+                }
+            }
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 if (valid[rr]) {
-                    p_next[rr] = ld2(prev + (off + sp + rr * rstep));
-                    c_next[rr] =
-                            *reinterpret_cast<const unsigned short*>(code + (koff + ksp + rr * krstep));
+                    const uint32_t o = rr * (4 * BOXX * 8);
+                    const double2 mid = tma::lds2(sm + o);
+                    const double l = tma::lds1(sm + o - 8);
+                    const double rgt = tma::lds1(sm + o + 16);
+                    const double2 u = tma::lds2(sm + o - BOXX * 8);
+                    const double2 d = tma::lds2(sm + o + BOXX * 8);
+                    const double2 below = tma::lds2(sb + o);
+                    const double2 above = tma::lds2(sa + o);
+                    update_pair<Cfg::FAST_DIV>(l, mid, rgt, u, d, below, above, p[rr], c[rr],
+                                               prev + (off + rr * rstep), bad);
                 }
             }
-        }
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            if (valid[rr]) {
-                const uint32_t o = rr * (4 * BOXX * 8);
-                const double2 mid = tma::lds2(sm + o);
-                const double l = tma::lds1(sm + o - 8);
-                const double rgt = tma::lds1(sm + o + 16);
-                const double2 u = tma::lds2(sm + o - BOXX * 8);
-                const double2 d = tma::lds2(sm + o + BOXX * 8);
-                const double2 below = tma::lds2(sb + o);
-                const double2 above = tma::lds2(sa + o);
-                update_pair<Cfg::FAST_DIV>(l, mid, rgt, u, d, below, above, p[rr], c[rr],
-                                           prev + (off + rr * rstep), bad);
+            off += sp;
+            koff += ksp;
+            // everyone is done with plane z-1: its buffer may be refilled
+            __syncthreads();
+            if (tid == 0 && issued < n_planes) {
+                // the freed stage gets the next plane; its barrier moves on to the next phase
+                tma::mbar_arrive_expect_tx(bars + 8 * st_b, Cfg::BOX_BYTES);
+                tma::load_box_3d(base + st_b * Cfg::STAGE_BYTES, &cur_map, bars + 8 * st_b, bx, by,
+                                 zs - 1 + issued);
+                ++issued;
+            }
+            st_b = st_m;
+            ++st_a;
+            if (st_a == NS) {
+                st_a = 0;
+                ph_a ^= 1u;
             }
         }
-        off += sp;
-        koff += ksp;
-        // everyone is done with plane z-1: its buffer may be refilled
-        __syncthreads();
-        if (tid == 0 && issued < n_planes) {
-            // the freed stage gets the next plane; its barrier moves on to the next phase
-            tma::mbar_arrive_expect_tx(bars + 8 * st_b, Cfg::BOX_BYTES);
-            tma::load_box_3d(base + st_b * Cfg::STAGE_BYTES, &cur_map, bars + 8 * st_b, bx, by,
-                             zs - 1 + issued);
-            ++issued;
-        }
-        st_b = st_m;
-        ++st_a;
-        if (st_a == NS) {
-            st_a = 0;
-            ph_a ^= 1u;
-        }
+        seq += (unsigned)n_planes;
+        if (!PERSIST) break;
     }
     raise_flags(bad, flag);
 }
