@@ -96,10 +96,14 @@ struct wvb_wg {
     int overlap = 1;
     int bminb = 8;
     int bthreads = 128;
-    int air_first = 0;
+    int air_first = 1;
     int persist = 0;
     int air_slots = 0;
     dev_buf<unsigned> work_counter;
+    dev_buf<uint32_t> step_counter;
+    int use_graph = 1;
+    cudaGraphExec_t step_graph = nullptr;  // two plain steps starting from P[0] = current
+
     int smem_pad = 0;  // extra dynamic shared memory per air CTA: caps CTAs/SM, leaving room for boundary CTAs
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
@@ -117,6 +121,7 @@ struct wvb_wg {
         if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (step_graph) cudaGraphExecDestroy(step_graph);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (stream_b) cudaStreamDestroy(stream_b);
@@ -585,7 +590,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     // ---- device state ------------------------------------------------------------
     int prio_lo = 0, prio_hi = 0;
     WVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    const int air_first = env_int("WVB_WG_AIRFIRST", 0);
+    const int air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, air_first ? prio_hi : prio_lo));
     WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_b, cudaStreamNonBlocking, air_first ? prio_lo : prio_hi));
     WVB_CUDA(cudaEventCreate(&w->ev0));
@@ -595,7 +600,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 8);
     w->bthreads = env_int("WVB_WG_BTHREADS", 128);
-    w->air_first = env_int("WVB_WG_AIRFIRST", 0);
+    w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);
@@ -629,6 +634,8 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->smem_pad = env_int("WVB_WG_SMEM_PAD", 0) & ~127;
     w->persist = env_int("WVB_WG_PERSIST", 0);
     w->work_counter.alloc(1, true, &w->device_bytes);
+    w->step_counter.alloc(1, true, &w->device_bytes);
+    w->use_graph = env_int("WVB_WG_GRAPH", 1) && d->nranks == 1;
     int slots;
     long long tiles;
     if (w->variant == WVB_WG_KERNEL_TMA) {
@@ -667,6 +674,60 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         nccl_check(nccl::get().CommInitRank(&w->comm, w->nranks, id, w->rank), "ncclCommInitRank");
     }
     WVB_CUDA(cudaDeviceSynchronize());
+}
+
+// ---- CUDA-graph batching of the step loop ------------------------------------------
+// A launch-bound mesh (BASELINE config 1: ~20 k nodes) spends its time in launch
+// overhead: memset + air kernel + boundary kernel + two event hops per step. Two
+// consecutive steps (the buffers swap roles every step, so two steps return to the
+// starting parity) are captured once into a graph and replayed. `body(i)` enqueues
+// step i's extra work (source / receivers); it must not depend on host state that
+// changes between replays.
+template <class Body>
+cudaGraphExec_t capture_two_steps(wvb_wg* w, Body&& body) {
+    cudaGraph_t graph = nullptr;
+    const int cur0 = w->cur;
+    const uint64_t launches0 = w->launches;
+    WVB_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        for (int i = 0; i < 2; ++i) {
+            body();
+            enqueue_step(w);
+        }
+    } catch (...) {
+        cudaStreamEndCapture(w->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        w->cur = cur0;
+        throw;
+    }
+    WVB_CUDA(cudaStreamEndCapture(w->stream, &graph));
+    w->cur = cur0;  // capturing enqueued nothing
+    w->launches = launches0;
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        set_last_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        throw status_error{WVB_ERR_CUDA};
+    }
+    return exec;
+}
+
+// n plain steps, through the two-step graph where possible
+void enqueue_steps(wvb_wg* w, uint32_t n) {
+    const uint64_t per_step = 1 + ((w->bl[0].n + w->bl[1].n + w->bl[2].n) ? 1 : 0);
+    if (w->use_graph && n >= 4) {
+        if (w->cur != 0) {  // the graph is captured for P[0] = current
+            enqueue_step(w);
+            --n;
+        }
+        if (!w->step_graph) w->step_graph = capture_two_steps(w, [] {});
+        for (; n >= 2; n -= 2) {
+            WVB_CUDA(cudaGraphLaunch(w->step_graph, w->stream));
+            w->launches += 2 * per_step;
+        }
+    }
+    for (; n; --n) enqueue_step(w);
 }
 
 template <class F>
@@ -809,7 +870,7 @@ wvb_status wvb_wg_step(wvb_wg* w, uint32_t n_steps, int32_t* error_flags) {
     wvb_status s = guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));  // waveguide.h:82
-        for (uint32_t i = 0; i < n_steps; ++i) enqueue_step(w);
+        enqueue_steps(w, n_steps);
         WVB_CUDA(cudaGetLastError());
         flags = fetch_flags(w);
     });
@@ -853,7 +914,7 @@ wvb_status wvb_wg_time_steps(wvb_wg* w, uint32_t n_steps, float* ms, int32_t* er
         WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
         WVB_CUDA(cudaStreamSynchronize(w->stream));
         WVB_CUDA(cudaEventRecord(w->ev0, w->stream));
-        for (uint32_t i = 0; i < n_steps; ++i) enqueue_step(w);
+        enqueue_steps(w, n_steps);
         WVB_CUDA(cudaEventRecord(w->ev1, w->stream));
         WVB_CUDA(cudaEventSynchronize(w->ev1));
         WVB_CUDA(cudaGetLastError());
@@ -953,20 +1014,55 @@ wvb_status wvb_wg_run(wvb_wg* w, const wvb_wg_run_params* p, uint32_t* steps_don
             d_out.alloc((size_t)p->n_steps * p->n_receivers, true);
         }
         WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
-        for (uint32_t step = 0; step < p->n_steps; ++step) {
+        WVB_CUDA(cudaMemsetAsync(w->step_counter.p, 0, sizeof(uint32_t), w->stream));
+        // one iteration of waveguide.h:80-124 before the kernel: pre (source), post's view
+        // (receivers read `current`, which the kernel does not modify), step counter
+        auto pre_post = [&] {
             double* cur = w->P[w->cur].p;
             if (n_src) {
-                wg_source<<<1, 32, 0, w->stream>>>(cur, d_src.p, n_src, d_signal.p, step, p->soft);
+                wg_source<<<1, 32, 0, w->stream>>>(cur, d_src.p, n_src, d_signal.p, w->step_counter.p,
+                                                   p->soft);
                 w->launches++;
             }
             if (p->n_receivers) {
                 wg_gather<<<(p->n_receivers + 127) / 128, 128, 0, w->stream>>>(
-                        cur, d_rcv.p, (int)p->n_receivers, d_out.p + (size_t)step * p->n_receivers);
+                        cur, d_rcv.p, (int)p->n_receivers, d_out.p, w->step_counter.p);
                 w->launches++;
             }
-            enqueue_step(w);
-            done = step + 1;
-            if (p->check_interval && (done % p->check_interval) == 0) {
+            wg_advance<<<1, 1, 0, w->stream>>>(w->step_counter.p);
+            w->launches++;
+        };
+        struct graph_holder {
+            cudaGraphExec_t g = nullptr;
+            ~graph_holder() {
+                if (g) cudaGraphExecDestroy(g);
+            }
+        } run_graph;
+        const uint64_t per_pair = 2 * (uint64_t)((n_src ? 1 : 0) + (p->n_receivers ? 1 : 0) + 1 + 1 +
+                                                 ((w->bl[0].n + w->bl[1].n + w->bl[2].n) ? 1 : 0));
+        const uint32_t ci = p->check_interval;
+        uint32_t step = 0;
+        while (step < p->n_steps) {
+            const uint32_t until = ci ? std::min(p->n_steps, (step / ci + 1) * ci) : p->n_steps;
+            if (w->use_graph && until - step >= 4) {
+                if (w->cur != 0) {
+                    pre_post();
+                    enqueue_step(w);
+                    ++step;
+                }
+                if (!run_graph.g) run_graph.g = capture_two_steps(w, pre_post);
+                for (; until - step >= 2; step += 2) {
+                    WVB_CUDA(cudaGraphLaunch(run_graph.g, w->stream));
+                    w->launches += per_pair;
+                    w->cur ^= 0;  // two steps: parity unchanged
+                }
+            }
+            for (; step < until; ++step) {
+                pre_post();
+                enqueue_step(w);
+            }
+            done = step;
+            if (ci && done < p->n_steps) {
                 flags = fetch_flags(w);
                 if (flags) break;
             }

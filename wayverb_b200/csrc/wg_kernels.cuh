@@ -668,20 +668,25 @@ wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList
 // ---------------------------------------------------------------------------
 // hard_source / soft_source (preprocessor/hard_source.h:17-23, soft_source.h:17-25)
 // applied to every local copy of the node (owned plane and/or ghost plane).
+// The step index lives in device memory so that a captured CUDA graph can be
+// replayed for any step.
 __global__ void wg_source(double* __restrict__ cur, const long long* __restrict__ offs, int n_offs,
-                          const double* __restrict__ signal, uint32_t step, int soft) {
+                          const double* __restrict__ signal, const uint32_t* __restrict__ step_ptr,
+                          int soft) {
     const int i = threadIdx.x;
     if (i < n_offs) {
-        const double v = signal[step];
+        const double v = signal[*step_ptr];
         cur[offs[i]] = soft ? cur[offs[i]] + v : v;
     }
 }
-// postprocessor::node (postprocessor/node.cpp:14-18) for n receivers; offs < 0 = not owned
+// postprocessor::node (postprocessor/node.cpp:14-18) for n receivers; offs < 0 = not owned.
+// out[step * n + i]
 __global__ void wg_gather(const double* __restrict__ cur, const long long* __restrict__ offs, int n,
-                          double* __restrict__ out) {
+                          double* __restrict__ out, const uint32_t* __restrict__ step_ptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
+    if (i < n) out[(size_t)(*step_ptr) * n + i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
 }
+__global__ void wg_advance(uint32_t* __restrict__ step_ptr) { *step_ptr += 1; }
 // error flag -> one int per bit, so that ranks can max-reduce it
 __global__ void flag_expand(const int* __restrict__ flag, int* __restrict__ out5) {
     const int i = threadIdx.x;
