@@ -46,7 +46,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc()]
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
-    cmd += NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-ldl"]
+    extra = os.environ.get("WVB_NVCC_DEFS", "").split()  # e.g. "-DRT_MIN_BLOCKS=8" for experiments
+    cmd += NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

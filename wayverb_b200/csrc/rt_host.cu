@@ -25,6 +25,8 @@ struct wvb_rt {
     dev_buf<float4> vertices;
     dev_buf<float> surfaces;
     dev_buf<rt::TriPre> pre;
+    dev_buf<uint2> cells;
+    dev_buf<rt::VoxEntry> entries;
     dev_buf<double> hist;
     dev_buf<unsigned long long> dropped;
     rt::Scene sc{};
@@ -125,8 +127,26 @@ wvb_status wvb_rt_create(const wvb_rt_scene_desc* d, wvb_rt** out) {
         r->dropped.alloc(1, true);
         rt::rt_precompute<<<(d->num_triangles + 127) / 128, 128, 0, r->stream>>>(
                 r->triangles.p, r->vertices.p, r->pre.p, d->num_triangles);
-        WVB_CUDA(cudaGetLastError());
-        WVB_CUDA(cudaStreamSynchronize(r->stream));
+        {
+            // first entry of every voxel's run (prefix sum of the run lengths, host side)
+            std::vector<uint32_t> first(cells);
+            uint64_t total = 0;
+            for (uint64_t c = 0; c < cells; ++c) {
+                first[c] = (uint32_t)total;
+                total += d->voxel_index[d->voxel_index[c]];
+            }
+            WVB_REQUIRE(total < 0xffffffffull, WVB_ERR_UNSUPPORTED, "voxel runs too long");
+            dev_buf<uint32_t> d_first;
+            d_first.upload(first.data(), first.size());
+            r->cells.alloc(cells, false);
+            r->entries.alloc(std::max<uint64_t>(total, 1), false);
+            rt::rt_build_entries<<<(unsigned)((cells + 127) / 128), 128, 0, r->stream>>>(
+                    r->voxel_index.p, r->pre.p, d_first.p, r->cells.p, r->entries.p, (uint32_t)cells);
+            WVB_CUDA(cudaGetLastError());
+            WVB_CUDA(cudaStreamSynchronize(r->stream));
+        }
+        r->sc.cells = r->cells.p;
+        r->sc.entries = r->entries.p;
         r->sc.voxel_index = r->voxel_index.p;
         r->sc.triangles = r->triangles.p;
         r->sc.pre = r->pre.p;

@@ -22,6 +22,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 6
+#endif
+
 namespace wvb {
 namespace rt {
 
@@ -50,8 +54,19 @@ struct alignas(16) TriPre {
     float e0x, e0y, e0z, ny;
     float e1x, e1y, e1z, nz;
 };
+// One entry of a voxel's triangle run, gathered at create time so that the walk
+// needs one dependent load per triangle instead of index -> triangle -> vertices:
+// the triangle's precomputed data next to its index (64 B, one 128-B line holds two).
+struct alignas(16) VoxEntry {
+    TriPre pre;
+    uint32_t tri;
+    uint32_t pad_[3];
+};
+static_assert(sizeof(VoxEntry) == 64, "VoxEntry size");
 
 struct Scene {
+    const uint2* cells;        // per voxel (x*side*side + y*side + z): first entry, entry count
+    const VoxEntry* entries;   // the runs of voxel_collection.cpp:9-37, in the same order
     const uint32_t* voxel_index;
     const TriPod* triangles;
     const TriPre* pre;
@@ -207,7 +222,7 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
     // voxel, or leaves the voxel -- identical visiting and testing order, identical
     // arithmetic, identical result.
     uint32_t i = 0, num = 0;
-    const uint32_t* begin = sc.voxel_index;
+    const VoxEntry* begin = sc.entries;
     float best_t = 0.0f, tmin = 0.0f;
     uint32_t best_i = 0;
     int min_i = 0;
@@ -218,19 +233,19 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
             tmin = tmx;
             if (tmy < tmin) { min_i = 1; tmin = tmy; }
             if (tmz < tmin) { min_i = 2; tmin = tmz; }
-            const uint32_t voxel_offset =
-                    sc.voxel_index[(size_t)ix * side * side + (size_t)iy * side + iz];
-            num = sc.voxel_index[voxel_offset];
-            begin = sc.voxel_index + voxel_offset + 1;
+            const uint2 cell = sc.cells[(size_t)ix * side * side + (size_t)iy * side + iz];
+            num = cell.y;
+            begin = sc.entries + cell.x;
             i = 0;
             best_t = 0.0f;
             enter = false;
         }
         if (i < num) {
-            const uint32_t ti = begin[i];
+            const uint32_t ti = begin[i].tri;
+            const TriPre& T = begin[i].pre;
             ++i;
             if (ti != avoid) {
-                const float t = tri_intersection(sc.pre[ti], pos, dir);
+                const float t = tri_intersection(T, pos, dir);
                 if (t && (!best_t || t < best_t)) {
                     best_i = ti;
                     best_t = t;
@@ -340,6 +355,27 @@ __global__ void rt_precompute(const TriPod* __restrict__ tris, const float4* __r
     }
 }
 
+// voxel runs -> (cells, entries)
+__global__ void rt_build_entries(const uint32_t* __restrict__ voxel_index, const TriPre* __restrict__ pre,
+                                 const uint32_t* __restrict__ first, uint2* __restrict__ cells,
+                                 VoxEntry* __restrict__ entries, uint32_t n_cells) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) {
+        const uint32_t off = voxel_index[c];
+        const uint32_t num = voxel_index[off];
+        const uint32_t e0 = first[c];
+        cells[c] = make_uint2(e0, num);
+        for (uint32_t i = 0; i < num; ++i) {
+            const uint32_t ti = voxel_index[off + 1 + i];
+            VoxEntry e;
+            e.pre = pre[ti];
+            e.tri = ti;
+            e.pad_[0] = e.pad_[1] = e.pad_[2] = 0;
+            entries[e0 + i] = e;
+        }
+    }
+}
+
 // directions from Philox stream 1 (random_unit_vector, core/azimuth_elevation.h:31-35)
 __global__ void rt_directions(unsigned long long seed, unsigned long long base, uint32_t n,
                               float* __restrict__ out3) {
@@ -370,7 +406,7 @@ __global__ void rt_closest_hit(Scene sc, const float* __restrict__ rays6, uint32
 
 // the whole life of one ray: raytracer.h:223-244 with reflections (program.cpp:59-153),
 // stochastic (stochastic/program.cpp:58-152) and the histogram processor folded in
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RT_MIN_BLOCKS)
 rt_trace(Scene sc, Params P, const float* __restrict__ dirs3, uint32_t n, double* __restrict__ hist,
          unsigned long long* __restrict__ dropped, ReflectionPod* __restrict__ refl_out) {
     const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
