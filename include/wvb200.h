@@ -340,6 +340,32 @@ float wvb_rt_ray_energy(uint64_t total_rays, const float source[3], const float 
  * voxel grid's diagonal */
 uint32_t wvb_rt_safe_bins(const wvb_rt* rt, uint32_t depth, double speed_of_sound, double rate);
 
+/* ---- mesh construction (the step before waveguide::run) ---------------------- */
+
+typedef struct wvb_mesh wvb_mesh;
+
+/* compute_mesh's node part (src/waveguide/src/mesh.cpp:53-141) on the device:
+ *   set_node_inside           mesh_setup_program.cpp:110-140 (voxel_inside, 32 probe rays)
+ *   set_node_boundary_type    mesh_setup_program.cpp:142-172
+ *   compute_boundary_index_data   boundary_coefficient_finder.cpp:39-132 with the
+ *       1d (closest triangle, brute force), 2d and 3d finders of
+ *       boundary_coefficient_program.cpp:310-484
+ * for the mesh_descriptor {min_corner, dim, spacing} (mesh_descriptor.h:14-20).
+ * scene: the voxelised scene (may be NULL when both `inside` and `surface_1d` are
+ * given). inside (optional): one byte per node, replaces set_node_inside.
+ * surface_1d (optional): per node, the surface the 1d finder would return.
+ * The result feeds wvb_wg_desc: nodes, boundary_index[3], boundary_count[3]. */
+wvb_status wvb_mesh_create(wvb_rt* scene, const float min_corner[3], const int32_t dim[3],
+                           float spacing, const uint8_t* inside, const uint32_t* surface_1d,
+                           int32_t device, wvb_mesh** out);
+void wvb_mesh_destroy(wvb_mesh* mesh);
+/* number of 1-d, 2-d and 3-d boundary nodes (= lengths of boundary_index_array_N) */
+wvb_status wvb_mesh_counts(const wvb_mesh* mesh, uint64_t counts[3]);
+/* copies out (each pointer optional): dim[0]*dim[1]*dim[2] condensed nodes,
+ * boundary_index_array_1/2/3 flattened, the inside mask */
+wvb_status wvb_mesh_read(const wvb_mesh* mesh, wvb_condensed_node* nodes, uint32_t* b1, uint32_t* b2,
+                         uint32_t* b3, uint8_t* inside);
+
 /* ---- test hooks ------------------------------------------------------------- */
 /* The reference's device filter test kernels (cl/filters.cpp:56-75): n_streams
  * parallel filters fed input[sample][stream] (float), output likewise.

@@ -276,6 +276,197 @@ inline inter_t voxel_traversal(const scene_t& sc, f3 pos, f3 dir, uint32_t avoid
     return inter_t{0, 0, 0, 0};
 }
 
+// count_intersections           voxel.cpp:97-133: number of triangle crossings along a
+// ray, ~0u if any crossing is degenerate (near an edge or vertex, geometry.cpp:13-18)
+inline uint32_t count_intersections(const scene_t& sc, f3 pos, f3 dir) {
+    const float sidef = float(sc.side);
+    const f3 vd = mk((sc.c1.x - sc.c0.x) / sidef, (sc.c1.y - sc.c0.y) / sidef,
+                     (sc.c1.z - sc.c0.z) / sidef);
+    const f3 rel = divv(sub(pos, sc.c0), vd);
+    int ind[3] = {int(std::floor(rel.x)), int(std::floor(rel.y)), int(std::floor(rel.z))};
+    const int side = int(sc.side);
+    uint32_t count = 0;
+    if (!(0 <= ind[0] && 0 <= ind[1] && 0 <= ind[2] && ind[0] < side && ind[1] < side &&
+          ind[2] < side)) {
+        return count;
+    }
+    const f3 lo = add(sc.c0, mulv(mk(float(ind[0]), float(ind[1]), float(ind[2])), vd));
+    const f3 hi = add(sc.c0, mulv(mk(float(ind[0] + 1), float(ind[1] + 1), float(ind[2] + 1)), vd));
+    int step[3], just_out[3];
+    float t_max[3], t_delta[3];
+    for (int i = 0; i < 3; ++i) {
+        const float d = comp(dir, i);
+        const bool neg = std::signbit(d);
+        step[i] = neg ? -1 : 1;
+        just_out[i] = neg ? -1 : side;
+        const float boundary = neg ? comp(lo, i) : comp(hi, i);
+        const float tmp = std::fabs((boundary - comp(pos, i)) / d);
+        t_max[i] = std::isnan(tmp) ? INFINITY : tmp;
+        t_delta[i] = std::fabs(comp(vd, i) / d);
+    }
+    float prev_max = 0;
+    for (;;) {
+        int min_i = 0;
+        for (int i = 1; i != 3; ++i) {
+            if (t_max[i] < t_max[min_i]) min_i = i;
+        }
+        const uint32_t voxel_offset =
+                sc.voxel_index[size_t(ind[0]) * side * side + size_t(ind[1]) * side + ind[2]];
+        const uint32_t num = sc.voxel_index[voxel_offset];
+        const uint32_t* begin = sc.voxel_index.data() + voxel_offset + 1;
+        const float max_dist = t_max[min_i];
+        for (uint32_t i = 0; i != num; ++i) {
+            const triangle_t tri = sc.triangles[begin[i]];
+            float t, u, v;
+            tri_intersection(sc.vert(tri.v0), sc.vert(tri.v1), sc.vert(tri.v2), pos, dir, &t, &u, &v);
+            if (t) {
+                // is_degenerate (geometry.cpp:13-18)
+                if (almost_equal(u, 0, ULP) || almost_equal(v, 0, ULP) || almost_equal(u + v, 1, ULP)) {
+                    return ~0u;
+                }
+                if (prev_max < t && t <= max_dist) count += 1;
+            }
+        }
+        ind[min_i] += step[min_i];
+        if (ind[min_i] == just_out[min_i]) break;
+        prev_max = t_max[min_i];
+        t_max[min_i] += t_delta[min_i];
+    }
+    return count;
+}
+
+// the 32 fixed probe directions of voxel_inside        voxel.cpp:156-189
+static const float kInsideDirections[32][3] = {
+        {-0.427602f, 0.791267f, -0.437096f},  {-0.832527f, -0.545442f, 0.0969113f},
+        {0.633363f, 0.413131f, 0.65435f},     {0.985873f, 0.140209f, 0.0916325f},
+        {0.384519f, 0.0309011f, -0.9226f},    {-0.532584f, -0.0244727f, 0.846023f},
+        {0.844848f, 0.230031f, -0.483029f},   {-0.186143f, -0.291698f, -0.938223f},
+        {-0.108511f, -0.861706f, 0.495669f},  {0.0951741f, 0.959367f, -0.265625f},
+        {0.407194f, 0.907127f, -0.106369f},   {0.521731f, -0.00522727f, -0.853094f},
+        {0.369627f, 0.218276f, 0.903179f},    {-0.518837f, 0.815586f, -0.25618f},
+        {-0.954901f, 0.105507f, 0.277548f},   {0.63419f, 0.768703f, 0.0830607f},
+        {-0.0258027f, 0.998294f, 0.052379f},  {-0.868361f, 0.473347f, 0.147958f},
+        {0.346294f, -0.131168f, 0.928911f},   {-0.635896f, 0.649019f, 0.417624f},
+        {0.293121f, 0.235495f, -0.926619f},   {-0.55088f, -0.0237137f, -0.834247f},
+        {-0.661022f, -0.653122f, -0.369434f}, {0.224176f, -0.351092f, 0.909109f},
+        {0.456587f, 0.736627f, -0.498907f},   {0.965231f, 0.154753f, 0.210667f},
+        {0.626034f, -0.245898f, 0.740011f},   {0.435825f, 0.794758f, -0.422393f},
+        {0.662049f, 0.713267f, 0.23009f},     {0.261843f, -0.620862f, 0.738897f},
+        {0.23673f, 0.714889f, 0.657946f},     {-0.404007f, 0.699316f, 0.589691f},
+};
+
+// voxel_inside + single_ray_inside     voxel.cpp:135-154,191-225
+inline bool voxel_inside(const scene_t& sc, f3 pt) {
+    for (int i = 0; i != 32; ++i) {
+        const f3 dir = mk(kInsideDirections[i][0], kInsideDirections[i][1], kInsideDirections[i][2]);
+        const uint32_t n = count_intersections(sc, pt, dir);
+        if (n == ~0u) continue;
+        return (n % 2) != 0;
+    }
+    return false;
+}
+
+// point_triangle_distance_squared      boundary_coefficient_program.cpp:16-135
+inline float point_triangle_distance_squared(f3 v0, f3 v1, f3 v2, f3 point) {
+    const f3 diff = sub(point, v0);
+    const f3 e0 = sub(v1, v0);
+    const f3 e1 = sub(v2, v0);
+    const float a00 = dot(e0, e0);
+    const float a01 = dot(e0, e1);
+    const float a11 = dot(e1, e1);
+    const float b0 = -dot(diff, e0);
+    const float b1 = -dot(diff, e1);
+    const float det = a00 * a11 - a01 * a01;
+    float t0 = a01 * b1 - a11 * b0;
+    float t1 = a01 * b0 - a00 * b1;
+    if (t0 + t1 <= det) {
+        if (t0 < 0) {
+            if (t1 < 0) {
+                if (b0 < 0) {
+                    t1 = 0;
+                    if (a00 <= -b0) t0 = 1;
+                    else t0 = -b0 / a00;
+                } else {
+                    t0 = 0;
+                    if (0 <= b1) t1 = 0;
+                    else if (a11 <= -b1) t1 = 1;
+                    else t1 = -b1 / a11;
+                }
+            } else {
+                t0 = 0;
+                if (0 <= b1) t1 = 0;
+                else if (a11 <= -b1) t1 = 1;
+                else t1 = -b1 / a11;
+            }
+        } else if (t1 < 0) {
+            t1 = 0;
+            if (0 <= b0) t0 = 0;
+            else if (a00 <= -b0) t0 = 1;
+            else t0 = -b0 / a00;
+        } else {
+            const float invDet = 1 / det;
+            t0 *= invDet;
+            t1 *= invDet;
+        }
+    } else {
+        if (t0 < 0) {
+            const float tmp0 = a01 + b0;
+            const float tmp1 = a11 + b1;
+            if (tmp0 < tmp1) {
+                const float numer = tmp1 - tmp0;
+                const float denom = a00 - 2 * a01 + a11;
+                if (denom <= numer) { t0 = 1; t1 = 0; }
+                else { t0 = numer / denom; t1 = 1 - t0; }
+            } else {
+                t0 = 0;
+                if (tmp1 <= 0) t1 = 1;
+                else if (0 <= b1) t1 = 0;
+                else t1 = -b1 / a11;
+            }
+        } else if (t1 < 0) {
+            const float tmp0 = a01 + b1;
+            const float tmp1 = a00 + b0;
+            if (tmp0 < tmp1) {
+                const float numer = tmp1 - tmp0;
+                const float denom = a00 - 2 * a01 + a11;
+                if (denom <= numer) { t1 = 1; t0 = 0; }
+                else { t1 = numer / denom; t0 = 1 - t1; }
+            } else {
+                t1 = 0;
+                if (tmp1 <= 0) t0 = 1;
+                else if (0 <= b0) t0 = 0;
+                else t0 = -b0 / a00;
+            }
+        } else {
+            const float numer = a11 + b1 - a01 - b0;
+            if (numer <= 0) { t0 = 0; t1 = 1; }
+            else {
+                const float denom = a00 - 2 * a01 + a11;
+                if (denom <= numer) { t0 = 1; t1 = 0; }
+                else { t0 = numer / denom; t1 = 1 - t0; }
+            }
+        }
+    }
+    const f3 closest = add(add(v0, mul(e0, t0)), mul(e1, t1));
+    const f3 d = sub(point, closest);
+    return dot(d, d);
+}
+
+// slow_closest_triangle         boundary_coefficient_program.cpp:222-241 (what the 1d finder uses, :338)
+inline uint32_t slow_closest_triangle(const scene_t& sc, f3 pt) {
+    uint32_t ret = 0;
+    float distance = INFINITY;
+    for (uint32_t i = 0; i != sc.triangles.size(); ++i) {
+        const triangle_t t = sc.triangles[i];
+        const float nd = point_triangle_distance_squared(sc.vert(t.v0), sc.vert(t.v1), sc.vert(t.v2), pt);
+        if (nd < distance) {
+            ret = i;
+            distance = nd;
+        }
+    }
+    return ret;
+}
+
 // voxel_point_intersection      voxel.cpp:227-258
 inline bool point_visible(const scene_t& sc, f3 begin, f3 point, uint32_t avoid) {
     const f3 b2p = sub(point, begin);
@@ -404,6 +595,30 @@ void rto_directions(uint64_t seed, uint64_t base, size_t n, float* out3) {
         direction_rng(seed, uint32_t(base + i), 0u, 1u, &z, &th);
         const f3 d = sphere_point(z, th);
         out3[3 * i] = d.x; out3[3 * i + 1] = d.y; out3[3 * i + 2] = d.z;
+    }
+}
+
+// set_node_inside (mesh_setup_program.cpp:110-140) for every node of a mesh
+// descriptor: position = min_corner + locator * spacing (cl/utils.cpp:71-74), float
+void rto_nodes_inside(const rto_scene* s, const float* min_corner, const int32_t* dim, float spacing,
+                      uint8_t* inside_out) {
+    const long long nn = (long long)dim[0] * dim[1] * dim[2];
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (long long i = 0; i < nn; ++i) {
+        const int x = int(i % dim[0]), y = int((i / dim[0]) % dim[1]), z = int(i / dim[0] / dim[1]);
+        const f3 p = mk(min_corner[0] + float(x) * spacing, min_corner[1] + float(y) * spacing,
+                        min_corner[2] + float(z) * spacing);
+        inside_out[i] = voxel_inside(s->sc, p) ? 1 : 0;
+    }
+}
+// the surface the 1d finder assigns to a node position (boundary_coefficient_program.cpp:323-342)
+void rto_closest_surface(const rto_scene* s, const float* points3, size_t n, uint32_t* surface_out,
+                         uint32_t* triangle_out) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; ++i) {
+        const uint32_t t = slow_closest_triangle(s->sc, mk(points3[3 * i], points3[3 * i + 1], points3[3 * i + 2]));
+        if (triangle_out) triangle_out[i] = t;
+        surface_out[i] = s->sc.triangles[t].surface;
     }
 }
 

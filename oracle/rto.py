@@ -51,6 +51,8 @@ def lib():
         L.rto_directions.argtypes = [C.c_uint64, C.c_uint64, sz, vp]
         L.rto_sincos.argtypes = [vp, sz, vp, vp]
         L.rto_lut_index.argtypes = [vp, sz, vp, vp]
+        L.rto_nodes_inside.argtypes = [vp, vp, vp, C.c_float, vp]
+        L.rto_closest_surface.argtypes = [vp, vp, sz, vp, vp]
         L.rto_trace.argtypes = [vp, vp, vp, sz, vp, vp, vp]
         L.rto_num_threads.restype = C.c_int
         L.rto_params_size.restype = sz
@@ -86,6 +88,22 @@ class Scene:
         t = np.zeros(n, np.float32)
         lib().rto_closest_hit(self._h, _p(rays), n, int(brute), _p(tri), _p(t))
         return tri, t
+
+    def nodes_inside(self, min_corner, dims, spacing):
+        """set_node_inside for a mesh descriptor -> bool array [z, y, x]"""
+        mc = np.asarray(min_corner, np.float32)
+        d = np.asarray(dims, np.int32)
+        out = np.zeros(int(d[0]) * int(d[1]) * int(d[2]), np.uint8)
+        lib().rto_nodes_inside(self._h, _p(mc), _p(d), float(spacing), _p(out))
+        return out.reshape(int(d[2]), int(d[1]), int(d[0])).astype(bool)
+
+    def closest_surface(self, points):
+        """the 1d finder: surface (and triangle) of the closest triangle per point"""
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        surf = np.zeros(p.shape[0], np.uint32)
+        tri = np.zeros(p.shape[0], np.uint32)
+        lib().rto_closest_surface(self._h, _p(p), p.shape[0], _p(surf), _p(tri))
+        return surf, tri
 
     def trace(self, dirs, source, receiver, depth, total_rays=None, receiver_radius=0.1, speed_of_sound=340.0,
               histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0, n_bins=None,

@@ -95,6 +95,8 @@ WG_SYMBOLS = [
     "wvb_mesh_cuboid", "wvb_version", "wvb_device_count", "wvb_last_error",
 ]
 
+MESH_SYMBOLS = ["wvb_mesh_create", "wvb_mesh_destroy", "wvb_mesh_counts", "wvb_mesh_read"]
+
 RT_SYMBOLS = [
     "wvb_rt_create", "wvb_rt_destroy", "wvb_rt_trace", "wvb_rt_read_histogram", "wvb_rt_reset_histogram",
     "wvb_rt_reflection_depth", "wvb_rt_ray_energy", "wvb_rt_safe_bins", "wvb_rt_closest_hit",
@@ -144,6 +146,12 @@ def lib():
     L.wvb_nccl_unique_id.argtypes = [vp, C.c_size_t]
     L.wvb_wg_get_info.argtypes = [vp, C.POINTER(WgInfo)]
     L.wvb_mesh_cuboid.argtypes = [C.POINTER(i32 * 3), i32, i32, vp, C.POINTER(u64 * 3)]
+    L.wvb_mesh_create.argtypes = [vp, C.POINTER(C.c_float * 3), C.POINTER(i32 * 3), C.c_float, vp, vp, i32,
+                                  C.POINTER(vp)]
+    L.wvb_mesh_destroy.argtypes = [vp]
+    L.wvb_mesh_destroy.restype = None
+    L.wvb_mesh_counts.argtypes = [vp, C.POINTER(u64 * 3)]
+    L.wvb_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
     L.wvb_rt_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(vp)]
     L.wvb_rt_destroy.argtypes = [vp]
     L.wvb_rt_destroy.restype = None

@@ -73,6 +73,12 @@ float ray_energy(uint64_t total_rays, const float* s, const float* r, float radi
 
 }  // namespace
 
+// device view of a scene handle for the mesh builder (mesh_host.cu)
+const rt::Scene* wvb_rt_device_scene(const wvb_rt* r, int* device) {
+    if (device) *device = r->dev;
+    return &r->sc;
+}
+
 extern "C" {
 
 wvb_status wvb_rt_create(const wvb_rt_scene_desc* d, wvb_rt** out) {

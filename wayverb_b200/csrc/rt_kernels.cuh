@@ -341,7 +341,7 @@ __device__ __forceinline__ void deposit(const Params& P, double* __restrict__ hi
 }
 
 // per-triangle precompute (same ops as triangle_normal / triangle_vert_intersection)
-__global__ void rt_precompute(const TriPod* __restrict__ tris, const float4* __restrict__ verts,
+static __global__ void rt_precompute(const TriPod* __restrict__ tris, const float4* __restrict__ verts,
                               TriPre* __restrict__ out, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -356,7 +356,7 @@ __global__ void rt_precompute(const TriPod* __restrict__ tris, const float4* __r
 }
 
 // voxel runs -> (cells, entries)
-__global__ void rt_build_entries(const uint32_t* __restrict__ voxel_index, const TriPre* __restrict__ pre,
+static __global__ void rt_build_entries(const uint32_t* __restrict__ voxel_index, const TriPre* __restrict__ pre,
                                  const uint32_t* __restrict__ first, uint2* __restrict__ cells,
                                  VoxEntry* __restrict__ entries, uint32_t n_cells) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,7 +377,7 @@ __global__ void rt_build_entries(const uint32_t* __restrict__ voxel_index, const
 }
 
 // directions from Philox stream 1 (random_unit_vector, core/azimuth_elevation.h:31-35)
-__global__ void rt_directions(unsigned long long seed, unsigned long long base, uint32_t n,
+static __global__ void rt_directions(unsigned long long seed, unsigned long long base, uint32_t n,
                               float* __restrict__ out3) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -391,7 +391,7 @@ __global__ void rt_directions(unsigned long long seed, unsigned long long base, 
 }
 
 // closest hit of n rays (test hook mirroring reflector_tests.cpp's comparison)
-__global__ void rt_closest_hit(Scene sc, const float* __restrict__ rays6, uint32_t n,
+static __global__ void rt_closest_hit(Scene sc, const float* __restrict__ rays6, uint32_t n,
                                uint32_t* __restrict__ tri_out, float* __restrict__ t_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -406,7 +406,7 @@ __global__ void rt_closest_hit(Scene sc, const float* __restrict__ rays6, uint32
 
 // the whole life of one ray: raytracer.h:223-244 with reflections (program.cpp:59-153),
 // stochastic (stochastic/program.cpp:58-152) and the histogram processor folded in
-__global__ void __launch_bounds__(128, RT_MIN_BLOCKS)
+static __global__ void __launch_bounds__(128, RT_MIN_BLOCKS)
 rt_trace(Scene sc, Params P, const float* __restrict__ dirs3, uint32_t n, double* __restrict__ hist,
          unsigned long long* __restrict__ dropped, ReflectionPod* __restrict__ refl_out) {
     const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;

@@ -108,6 +108,35 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
+def build_mesh(dims, min_corner, spacing, coeffs, scene=None, inside=None, surface_1d=None, device=0,
+               return_inside=False):
+    """compute_mesh's node part (mesh.cpp:53-141) on the device -> Mesh.
+    scene: a RayTracer (the voxelised scene) or None when `inside` and `surface_1d`
+    (arrays indexed like the mesh, x fastest) are given."""
+    dx, dy, dz = (int(d) for d in dims)
+    mc = (C.c_float * 3)(*[float(v) for v in min_corner])
+    d3 = (C.c_int32 * 3)(dx, dy, dz)
+    ins = None if inside is None else np.ascontiguousarray(inside, np.uint8).reshape(-1)
+    s1 = None if surface_1d is None else np.ascontiguousarray(surface_1d, np.uint32).reshape(-1)
+    h = C.c_void_p()
+    check(lib().wvb_mesh_create(scene._h if scene is not None else None, C.byref(mc), C.byref(d3),
+                                float(spacing), ptr(ins) if ins is not None else None,
+                                ptr(s1) if s1 is not None else None, int(device), C.byref(h)))
+    try:
+        counts = (C.c_uint64 * 3)()
+        check(lib().wvb_mesh_counts(h, C.byref(counts)))
+        n1, n2, n3 = (int(c) for c in counts)
+        nodes = np.zeros(dx * dy * dz, NODE_DT)
+        b1, b2, b3 = np.zeros(max(n1, 1), np.uint32), np.zeros(max(n2, 1) * 2, np.uint32), \
+            np.zeros(max(n3, 1) * 3, np.uint32)
+        mask = np.zeros(dx * dy * dz, np.uint8)
+        check(lib().wvb_mesh_read(h, ptr(nodes), ptr(b1), ptr(b2), ptr(b3), ptr(mask)))
+    finally:
+        lib().wvb_mesh_destroy(h)
+    m = Mesh(dims, nodes, coeffs, b1[:n1], b2[:n2 * 2], b3[:n3 * 3])
+    return (m, mask.reshape(dz, dy, dx)) if return_inside else m
+
+
 class Waveguide:
     """One `wvb_wg` handle: a z-slab of the mesh on one GPU."""
 
