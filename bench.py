@@ -48,7 +48,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+    nvidia-smi needs ~1 s before its first line, so it is started before the warm-up and
+    every line is stamped with the host clock; stop(t0, t1) keeps the samples that fell
+    inside the timed region [t0, t1] (perf_counter seconds)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,7 +63,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -69,31 +72,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        t_end = time.perf_counter() + timeout
+        while not self.rows and time.perf_counter() < t_end and self.proc:
+            time.sleep(0.02)
+
+    def stop(self, t0, t1):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
+        for ts, r in self.rows:
+            if len(r) < 7 or not (t0 <= ts <= t1):
                 continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
             except ValueError:
                 continue
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_baseline(seconds_target=12.0):
@@ -155,7 +164,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", default="512,512,512", help="per-GPU slab (x,y,z planes per GPU)")
@@ -206,17 +215,19 @@ def main():
     wg.write(src, 1.0)
 
     # ---- kernel-resident timing: K steps, inputs already in HBM -----------------
-    wg.time_steps(args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    wg.time_steps(args.warmup)
+    sampler.wait_first_sample()
+    barrier()
     l0 = wg.info()["kernel_launches"]
     t0 = time.perf_counter()
     ms, flags = wg.time_steps(args.steps)
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    t1 = time.perf_counter()
+    wall_ms = (t1 - t0) * 1e3
     launches = wg.info()["kernel_launches"] - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t1)
     assert flags == 0, "simulation raised error flags 0x%x" % flags
 
     # ---- end to end through the step-wise C ABI with host buffers ------------------
