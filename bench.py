@@ -135,24 +135,36 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import wgo
-    dims = (512, 512, 64)
-    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [plaster_coeffs(wgo.COEFF_DT)])
-    sim = wgo.Sim(om, "float")
-    sim.write(om.index(256, 256, 32), 1.0)
+
+    def make(nz):
+        dims = (512, 512, nz)
+        om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [plaster_coeffs(wgo.COEFF_DT)])
+        sim = wgo.Sim(om, "float")
+        sim.write(om.index(256, 256, nz // 2), 1.0)
+        return dims, sim
+
+    # size the per-step sample so that K + W steps finish in about 90 s on this host
+    dims, sim = make(8)
+    sim.step(1)
+    t0 = time.perf_counter()
+    sim.step(2)
+    per_plane = (time.perf_counter() - t0) / 2 / dims[2]
+    nz = int(max(8, min(64, 90.0 / max(per_plane * (args.steps + args.warmup), 1e-9))))
+    dims, sim = make(nz)
     sim.step(args.warmup)
     t0 = time.perf_counter()
     sim.step(args.steps)
     dt = time.perf_counter() - t0
     nodes = dims[0] * dims[1] * dims[2]
     v = nodes * args.steps / dt / 1e6
-    sample = ("512x512x64 slab sample of the 512^3 plaster mesh per step; oracle port of "
-              "condensed_waveguide, float pressures + double filters, OpenMP")
+    sample = ("512x512x%d slab sample of the 512^3 plaster mesh per step; oracle port of "
+              "condensed_waveguide, float pressures + double filters, OpenMP" % nz)
     line = {
         "impl": "reference", "metric": "Mnode-updates/s (fp64)", "value": v, "unit": "Mnode-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64 filters",
         "data": "synthetic",
-        "config": {"workload": "512^3 cuboid, plaster 6th-order LRS walls (sampled: 512x512x64 slab per step)"},
+        "config": {"workload": "512^3 cuboid, plaster 6th-order LRS walls (sampled: 512x512x%d slab per step)" % nz},
         "cpu_baseline": {"value": v, "unit": "Mnode-updates/s", "cores": wgo.num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "Mnode-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

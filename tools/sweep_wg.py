@@ -27,13 +27,10 @@ def main():
     m = wvb.cuboid_mesh(dims, [plaster()])
     nodes = dims[0] * dims[1] * dims[2]
     configs = []
-    base = dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_MINB=1, WVB_WG_DIV=1, WVB_WG_STAGES=5, WVB_WG_BTHREADS=128,
-                WVB_WG_BMINB=8)
-    for ps, zc, af, ov in ((0, 12, 1, 1), (1, 12, 1, 1), (1, 24, 1, 1), (1, 37, 1, 1), (1, 16, 1, 1), (1, 24, 0, 1),
-                           (1, 24, 1, 0), (1, 64, 1, 1)):
-        configs.append(dict(base, WVB_WG_PERSIST=ps, WVB_WG_ZCHUNKS=zc, WVB_WG_AIRFIRST=af, WVB_WG_OVERLAP=ov))
-    configs.append(dict(base, WVB_WG_PERSIST=1, WVB_WG_ZCHUNKS=24, WVB_WG_AIRFIRST=1, WVB_WG_OVERLAP=1,
-                        WVB_WG_BTHREADS=64, WVB_WG_BMINB=16))
+    base = dict(WVB_WG_KERNEL="tma", WVB_WG_TY=8, WVB_WG_MINB=1, WVB_WG_DIV=1, WVB_WG_STAGES=5, WVB_WG_ZCHUNKS=12,
+                WVB_WG_OVERLAP=1)
+    for bp, af in ((0, 1), (1, 0), (2, 0), (1, 1), (4, 0), (3, 0)):
+        configs.append(dict(base, WVB_WG_BPERSIST=bp, WVB_WG_AIRFIRST=af))
     only = os.environ.get("SWEEP_ONLY")
     for cfg in configs:
         if only and cfg["WVB_WG_KERNEL"] != only:

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwvb200.so")
+LIB_PATH = os.environ.get("WVB_LIB") or os.path.join(HERE, "libwvb200.so")  # WVB_LIB: experiment builds
 
 # numpy views of the reference PODs (see include/wvb200.h for file:line)
 NODE_DT = np.dtype([("boundary_type", "<i4"), ("boundary_index", "<u4")])

@@ -61,13 +61,18 @@ __device__ __forceinline__ float tri_intersection_uv(const rt::TriPre& T, f3 pos
 // count_intersections (voxel.cpp:97-133) as the same flat state machine as the ray
 // kernel's walk: ~0u when a crossing is degenerate.
 __device__ __forceinline__ uint32_t count_intersections(const rt::Scene& sc, f3 pos, f3 dir) {
+    const unsigned lanes = __activemask();
+    bool done = false;
     const float sidef = (float)sc.side;
     const f3 vd = mk((sc.c1.x - sc.c0.x) / sidef, (sc.c1.y - sc.c0.y) / sidef,
                      (sc.c1.z - sc.c0.z) / sidef);
     const f3 rel = mk((pos.x - sc.c0.x) / vd.x, (pos.y - sc.c0.y) / vd.y, (pos.z - sc.c0.z) / vd.z);
     int ix = (int)floorf(rel.x), iy = (int)floorf(rel.y), iz = (int)floorf(rel.z);
     const int side = (int)sc.side;
-    if (!(0 <= ix && 0 <= iy && 0 <= iz && ix < side && iy < side && iz < side)) return 0u;
+    if (!(0 <= ix && 0 <= iy && 0 <= iz && ix < side && iy < side && iz < side)) {
+        done = true;
+        ix = iy = iz = 0;
+    }
     const f3 lo = mk(sc.c0.x + (float)ix * vd.x, sc.c0.y + (float)iy * vd.y, sc.c0.z + (float)iz * vd.z);
     const f3 hi = mk(sc.c0.x + (float)(ix + 1) * vd.x, sc.c0.y + (float)(iy + 1) * vd.y,
                      sc.c0.z + (float)(iz + 1) * vd.z);
@@ -86,48 +91,52 @@ __device__ __forceinline__ uint32_t count_intersections(const rt::Scene& sc, f3 
     float prev_max = 0.0f, tmin = 0.0f;
     int min_i = 0;
     bool enter = true;
-    for (;;) {
-        if (enter) {
-            min_i = 0;
-            tmin = tmx;
-            if (tmy < tmin) { min_i = 1; tmin = tmy; }
-            if (tmz < tmin) { min_i = 2; tmin = tmz; }
-            const uint2 cell = sc.cells[(size_t)ix * side * side + (size_t)iy * side + iz];
-            num = cell.y;
-            begin = sc.entries + cell.x;
-            i = 0;
-            enter = false;
-        }
-        if (i < num) {
-            float u, v;
-            const float t = tri_intersection_uv(begin[i].pre, pos, dir, u, v);
-            ++i;
-            if (t) {
-                if (rt::almost_equal(u, 0, 10.0f) || rt::almost_equal(v, 0, 10.0f) ||
-                    rt::almost_equal(u + v, 1, 10.0f)) {
-                    return ~0u;
+    while (__any_sync(lanes, !done)) {  // vote = convergence point, see rt::voxel_traversal
+        if (!done) {
+            if (enter) {
+                min_i = 0;
+                tmin = tmx;
+                if (tmy < tmin) { min_i = 1; tmin = tmy; }
+                if (tmz < tmin) { min_i = 2; tmin = tmz; }
+                const uint2 cell = sc.cells[(size_t)ix * side * side + (size_t)iy * side + iz];
+                num = cell.y;
+                begin = sc.entries + cell.x;
+                i = 0;
+                enter = false;
+            }
+            if (i < num) {
+                float u, v;
+                const float t = tri_intersection_uv(begin[i].pre, pos, dir, u, v);
+                ++i;
+                if (t) {
+                    if (rt::almost_equal(u, 0, 10.0f) || rt::almost_equal(v, 0, 10.0f) ||
+                        rt::almost_equal(u + v, 1, 10.0f)) {
+                        count = ~0u;  // degenerate crossing: this probe direction is undecided
+                        done = true;
+                    } else if (prev_max < t && t <= tmin) {
+                        count += 1;
+                    }
                 }
-                if (prev_max < t && t <= tmin) count += 1;
             }
-        }
-        if (i >= num) {
-            if (min_i == 0) {
-                ix += stx;
-                if (ix == jox) break;
-                prev_max = tmx;
-                tmx += tdx;
-            } else if (min_i == 1) {
-                iy += sty;
-                if (iy == joy) break;
-                prev_max = tmy;
-                tmy += tdy;
-            } else {
-                iz += stz;
-                if (iz == joz) break;
-                prev_max = tmz;
-                tmz += tdz;
+            if (!done && i >= num) {
+                if (min_i == 0) {
+                    ix += stx;
+                    if (ix == jox) done = true;
+                    prev_max = tmx;
+                    tmx += tdx;
+                } else if (min_i == 1) {
+                    iy += sty;
+                    if (iy == joy) done = true;
+                    prev_max = tmy;
+                    tmy += tdy;
+                } else {
+                    iz += stz;
+                    if (iz == joz) done = true;
+                    prev_max = tmz;
+                    tmz += tdz;
+                }
+                enter = true;
             }
-            enter = true;
         }
     }
     return count;

@@ -23,7 +23,7 @@
 #include <stdint.h>
 
 #ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 6
+#define RT_MIN_BLOCKS 8
 #endif
 
 namespace wvb {
@@ -194,13 +194,22 @@ __device__ __forceinline__ float tri_intersection(const TriPre& T, f3 pos, f3 di
 __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir, uint32_t avoid,
                                                  uint32_t& index, float t_stop = INFINITY) {
     index = 0;
+    // lanes that entered together leave together: the loop below is paced by a
+    // warp vote, so every iteration all unfinished lanes do one unit of work side by
+    // side (see the note at the loop)
+    const unsigned lanes = __activemask();
+    bool done = false;
+    float result = 0.0f;
     const float sidef = (float)sc.side;
     const f3 vd = mk((sc.c1.x - sc.c0.x) / sidef, (sc.c1.y - sc.c0.y) / sidef,
                      (sc.c1.z - sc.c0.z) / sidef);
     const f3 rel = mk((pos.x - sc.c0.x) / vd.x, (pos.y - sc.c0.y) / vd.y, (pos.z - sc.c0.z) / vd.z);
     int ix = (int)floorf(rel.x), iy = (int)floorf(rel.y), iz = (int)floorf(rel.z);
     const int side = (int)sc.side;
-    if (!(0 <= ix && 0 <= iy && 0 <= iz && ix < side && iy < side && iz < side)) return 0.0f;
+    if (!(0 <= ix && 0 <= iy && 0 <= iz && ix < side && iy < side && iz < side)) {
+        done = true;
+        ix = iy = iz = 0;
+    }
     const f3 lo = mk(sc.c0.x + (float)ix * vd.x, sc.c0.y + (float)iy * vd.y, sc.c0.z + (float)iz * vd.z);
     const f3 hi = mk(sc.c0.x + (float)(ix + 1) * vd.x, sc.c0.y + (float)(iy + 1) * vd.y,
                      sc.c0.z + (float)(iz + 1) * vd.z);
@@ -220,61 +229,68 @@ __device__ __forceinline__ float voxel_traversal(const Scene& sc, f3 pos, f3 dir
     // times. The same walk is therefore run as a flat state machine: every
     // iteration a lane either enters a voxel, tests ONE triangle of the current
     // voxel, or leaves the voxel -- identical visiting and testing order, identical
-    // arithmetic, identical result.
+    // arithmetic, identical result. The vote in the loop condition is a convergence
+    // point: without it the compiler threads the branches back into the nested
+    // loops.
     uint32_t i = 0, num = 0;
     const VoxEntry* begin = sc.entries;
     float best_t = 0.0f, tmin = 0.0f;
     uint32_t best_i = 0;
     int min_i = 0;
     bool enter = true;
-    for (;;) {
-        if (enter) {
-            min_i = 0;
-            tmin = tmx;
-            if (tmy < tmin) { min_i = 1; tmin = tmy; }
-            if (tmz < tmin) { min_i = 2; tmin = tmz; }
-            const uint2 cell = sc.cells[(size_t)ix * side * side + (size_t)iy * side + iz];
-            num = cell.y;
-            begin = sc.entries + cell.x;
-            i = 0;
-            best_t = 0.0f;
-            enter = false;
-        }
-        if (i < num) {
-            const uint32_t ti = begin[i].tri;
-            const TriPre& T = begin[i].pre;
-            ++i;
-            if (ti != avoid) {
-                const float t = tri_intersection(T, pos, dir);
-                if (t && (!best_t || t < best_t)) {
-                    best_i = ti;
-                    best_t = t;
+    while (__any_sync(lanes, !done)) {
+        if (!done) {
+            if (enter) {
+                min_i = 0;
+                tmin = tmx;
+                if (tmy < tmin) { min_i = 1; tmin = tmy; }
+                if (tmz < tmin) { min_i = 2; tmin = tmz; }
+                const uint2 cell = sc.cells[(size_t)ix * side * side + (size_t)iy * side + iz];
+                num = cell.y;
+                begin = sc.entries + cell.x;
+                i = 0;
+                best_t = 0.0f;
+                enter = false;
+            }
+            if (i < num) {
+                const uint32_t ti = begin[i].tri;
+                const TriPre& T = begin[i].pre;
+                ++i;
+                if (ti != avoid) {
+                    const float t = tri_intersection(T, pos, dir);
+                    if (t && (!best_t || t < best_t)) {
+                        best_i = ti;
+                        best_t = t;
+                    }
+                }
+            }
+            if (i >= num) {
+                if (best_t && best_t <= tmin) {
+                    index = best_i;
+                    result = best_t;
+                    done = true;
+                } else if (tmin > t_stop) {
+                    done = true;  // the next voxel starts beyond the point of interest
+                } else {
+                    if (min_i == 0) {
+                        ix += stx;
+                        if (ix == jox) done = true;
+                        tmx += tdx;
+                    } else if (min_i == 1) {
+                        iy += sty;
+                        if (iy == joy) done = true;
+                        tmy += tdy;
+                    } else {
+                        iz += stz;
+                        if (iz == joz) done = true;
+                        tmz += tdz;
+                    }
+                    enter = true;
                 }
             }
         }
-        if (i >= num) {
-            if (best_t && best_t <= tmin) {
-                index = best_i;
-                return best_t;
-            }
-            if (tmin > t_stop) break;  // the next voxel starts beyond the point of interest
-            if (min_i == 0) {
-                ix += stx;
-                if (ix == jox) break;
-                tmx += tdx;
-            } else if (min_i == 1) {
-                iy += sty;
-                if (iy == joy) break;
-                tmy += tdy;
-            } else {
-                iz += stz;
-                if (iz == joz) break;
-                tmz += tdz;
-            }
-            enter = true;
-        }
     }
-    return 0.0f;
+    return result;
 }
 
 // voxel_point_intersection      voxel.cpp:227-258

@@ -96,6 +96,7 @@ struct wvb_wg {
     int overlap = 1;
     int bminb = 8;
     int bthreads = 128;
+    int bpersist = 0;  // > 0: boundary kernel as a resident grid of bpersist CTAs per SM
     int air_first = 1;
     int persist = 0;
     int air_slots = 0;
@@ -358,6 +359,18 @@ void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t 
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
+    if (w->bpersist > 0) {
+        auto L = [&](int k) {
+            auto& l = w->bl[k];
+            return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
+        };
+        const uint32_t total = w->bl[0].n + w->bl[1].n + w->bl[2].n;
+        const uint32_t grid = std::min<uint32_t>((total + 127) / 128, (uint32_t)(w->bpersist * w->sm_count));
+        wg_boundary_strided<128, 8><<<grid, 128, 0, st>>>(cur, prev, L(0), L(1), L(2), w->coeffs.p, w->g,
+                                                          w->courant, w->courant_sq, w->flag.p);
+        w->launches++;
+        return;
+    }
     if (w->bthreads == 64) {
         if (w->bminb >= 16) launch_boundary_t<64, 16>(w, cur, prev, st);
         else launch_boundary_t<64, 10>(w, cur, prev, st);
@@ -600,6 +613,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 8);
     w->bthreads = env_int("WVB_WG_BTHREADS", 128);
+    w->bpersist = env_int("WVB_WG_BPERSIST", 0);
     w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);

@@ -663,6 +663,30 @@ wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList
     raise_flags(bad, flag);
 }
 
+// The same work as a grid-stride loop over the concatenated lists, for a grid of
+// a few CTAs per SM that stays resident for the whole step: launched BEFORE the air
+// kernel it takes one small slice of every SM's registers, the air kernel's CTAs
+// fill the rest, and the latency-bound boundary walk hides behind the
+// bandwidth-bound stencil instead of running after it.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+wg_boundary_strided(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
+                    BList L3, const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g,
+                    double courant, double courant_sq, int* __restrict__ flag) {
+    int bad = 0;
+    const uint32_t total = L1.n + L2.n + L3.n;
+    for (uint32_t t = blockIdx.x * THREADS + threadIdx.x; t < total; t += gridDim.x * THREADS) {
+        if (t < L1.n) {
+            bad |= boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
+        } else if (t < L1.n + L2.n) {
+            bad |= boundary_node<2>(cur, prev, L2, t - L1.n, coeffs, g, courant, courant_sq);
+        } else {
+            bad |= boundary_node<3>(cur, prev, L3, t - L1.n - L2.n, coeffs, g, courant, courant_sq);
+        }
+    }
+    raise_flags(bad, flag);
+}
+
 // ---------------------------------------------------------------------------
 // small helpers: source injection, receiver gather, fp32 conversion
 // ---------------------------------------------------------------------------
