@@ -95,17 +95,11 @@ struct wvb_wg {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
     int bminb = 8;
-    int bthreads = 128;
-    int bpersist = 0;  // > 0: boundary kernel as a resident grid of bpersist CTAs per SM
     int air_first = 1;
-    int persist = 0;
-    int air_slots = 0;
-    dev_buf<unsigned> work_counter;
     dev_buf<uint32_t> step_counter;
     int use_graph = 1;
     cudaGraphExec_t step_graph = nullptr;  // two plain steps starting from P[0] = current
 
-    int smem_pad = 0;  // extra dynamic shared memory per air CTA: caps CTAs/SM, leaving room for boundary CTAs
     CUtensorMap map[2];
     int variant = WVB_WG_KERNEL_DIRECT;
     int ty = 8, nstage = 5, zchunks = 1;
@@ -222,22 +216,15 @@ inline int node_class(int32_t bt, int* ndims) {
 
 // ---- launch configuration ------------------------------------------------------
 template <class Cfg>
-void set_tma_attr(int pad) {
-    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)Cfg::SMEM_BYTES + pad));
-    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)Cfg::SMEM_BYTES + pad));
+void set_tma_attr() {
+    WVB_CUDA(cudaFuncSetAttribute(wg_air_tma<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
 }
 template <class Cfg>
-int tma_occupancy(int pad, bool persist) {
+int tma_occupancy() {
     int nb = 0;
-    if (persist) {
-        WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg, true>, Cfg::THREADS,
-                                                               Cfg::SMEM_BYTES + pad));
-    } else {
-        WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg, false>, Cfg::THREADS,
-                                                               Cfg::SMEM_BYTES + pad));
-    }
+    WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wg_air_tma<Cfg>, Cfg::THREADS,
+                                                           Cfg::SMEM_BYTES));
     return nb;
 }
 
@@ -281,30 +268,16 @@ void launch_tma(wvb_wg* w, const double* cur, double* prev) {
     (void)cur;  // read through the tensor map of P[w->cur]
     const int tiles_x = (g.dx + Cfg::TX - 1) / Cfg::TX, tiles_y = (g.dy + Cfg::TY - 1) / Cfg::TY;
     const unsigned items = (unsigned)tiles_x * tiles_y * w->zchunks;
-    const size_t smem = Cfg::SMEM_BYTES + w->smem_pad;
-    if (w->persist) {
-        WVB_CUDA(cudaMemsetAsync(w->work_counter.p, 0, sizeof(unsigned), w->stream));
-        const unsigned grid = std::min<unsigned>(items, (unsigned)w->air_slots);
-        wg_air_tma<Cfg, true><<<grid, Cfg::THREADS, smem, w->stream>>>(
-                w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->work_counter.p,
-                w->flag.p);
-    } else {
-        wg_air_tma<Cfg, false><<<items, Cfg::THREADS, smem, w->stream>>>(
-                w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->work_counter.p,
-                w->flag.p);
-    }
+    wg_air_tma<Cfg><<<items, Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
+            w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->flag.p);
 }
 
 // the TMA configurations that are compiled in: (TY, stages, fast division, min CTAs/SM)
 #define WVB_TMA_CONFIGS(X) \
     X(8, 5, true, 1)       \
     X(8, 5, false, 1)      \
-    X(8, 5, true, 4)       \
     X(8, 4, true, 1)       \
-    X(8, 4, true, 4)       \
     X(8, 6, true, 1)       \
-    X(8, 7, true, 1)       \
-    X(8, 8, true, 1)       \
     X(16, 5, true, 1)
 
 template <class F>
@@ -359,27 +332,8 @@ void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t 
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
-    if (w->bpersist > 0) {
-        auto L = [&](int k) {
-            auto& l = w->bl[k];
-            return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
-        };
-        const uint32_t total = w->bl[0].n + w->bl[1].n + w->bl[2].n;
-        const uint32_t grid = std::min<uint32_t>((total + 127) / 128, (uint32_t)(w->bpersist * w->sm_count));
-        wg_boundary_strided<128, 8><<<grid, 128, 0, st>>>(cur, prev, L(0), L(1), L(2), w->coeffs.p, w->g,
-                                                          w->courant, w->courant_sq, w->flag.p);
-        w->launches++;
-        return;
-    }
-    if (w->bthreads == 64) {
-        if (w->bminb >= 16) launch_boundary_t<64, 16>(w, cur, prev, st);
-        else launch_boundary_t<64, 10>(w, cur, prev, st);
-    } else if (w->bthreads == 32) {
-        launch_boundary_t<32, 32>(w, cur, prev, st);
-    } else {
-        if (w->bminb >= 8) launch_boundary_t<128, 8>(w, cur, prev, st);
-        else launch_boundary_t<128, 5>(w, cur, prev, st);
-    }
+    if (w->bminb >= 8) launch_boundary_t<128, 8>(w, cur, prev, st);
+    else launch_boundary_t<128, 5>(w, cur, prev, st);
     w->launches++;
 }
 
@@ -612,8 +566,6 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 8);
-    w->bthreads = env_int("WVB_WG_BTHREADS", 128);
-    w->bpersist = env_int("WVB_WG_BPERSIST", 0);
     w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
@@ -644,10 +596,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->nstage = env_int("WVB_WG_STAGES", 5);
     w->fast_div = env_int("WVB_WG_DIV", 1) ? 1 : 0;
     w->pf = env_int("WVB_WG_PF", 4);
-    w->minb = env_int("WVB_WG_MINB", 1);
-    w->smem_pad = env_int("WVB_WG_SMEM_PAD", 0) & ~127;
-    w->persist = env_int("WVB_WG_PERSIST", 0);
-    w->work_counter.alloc(1, true, &w->device_bytes);
+    w->minb = 1;
     w->step_counter.alloc(1, true, &w->device_bytes);
     w->use_graph = env_int("WVB_WG_GRAPH", 1) && d->nranks == 1;
     int slots;
@@ -656,21 +605,20 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         int occ = 0;
         const bool known = with_tma_cfg(w, [&](auto cfg) {
             using Cfg = decltype(cfg);
-            set_tma_attr<Cfg>(w->smem_pad);
-            occ = tma_occupancy<Cfg>(w->smem_pad, w->persist != 0);
+            set_tma_attr<Cfg>();
+            occ = tma_occupancy<Cfg>();
         });
         if (!known) {  // unknown combination: fall back to the default configuration
             w->ty = 8; w->nstage = 5; w->fast_div = 1; w->minb = 1;
             with_tma_cfg(w, [&](auto cfg) {
                 using Cfg = decltype(cfg);
-                set_tma_attr<Cfg>(w->smem_pad);
-                occ = tma_occupancy<Cfg>(w->smem_pad, w->persist != 0);
+                set_tma_attr<Cfg>();
+                occ = tma_occupancy<Cfg>();
             });
         }
         make_tensor_map(w, 0, w->ty);
         make_tensor_map(w, 1, w->ty);
         slots = std::max(1, occ) * w->sm_count;
-        w->air_slots = slots;
         tiles = (long long)((dx + 127) / 128) * ((dy + w->ty - 1) / w->ty);
     } else {
         slots = 4 * w->sm_count;

@@ -307,26 +307,22 @@ struct TmaCfg {
     static_assert(NSTAGE >= 4, "need 3 live planes + at least one in flight");
 };
 
-// Work item = (x tile, y tile, z chunk), numbered x fastest. PERSIST = false:
-// one item per CTA (grid = number of items). PERSIST = true: the grid is the
-// number of CTAs that fit on the chip and every CTA pulls items from a global
-// counter until none are left; all CTAs are then resident from the start, which
-// lets the (register-light) boundary kernel on the second stream occupy the
-// resources they leave over, instead of queueing behind ~3000 waiting CTAs.
-template <class Cfg, bool PERSIST>
+// Work item = (x tile, y tile, z chunk), numbered x fastest, one per CTA.
+// (A persistent variant that pulled items from a global counter, so that the
+// boundary kernel could share the SMs for the whole step, measured 15 % slower
+// and was dropped; see profiles/r01_experiments.md.)
+template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ prev,
            const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y, int zchunks,
-           unsigned int* __restrict__ work_counter, int* __restrict__ flag) {
+           int* __restrict__ flag) {
     constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
     constexpr int R = Cfg::ROWS_PER_THREAD;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ unsigned int s_item;
     // 128-byte aligned stage ring followed by the mbarriers (shared-window addresses)
     const uint32_t base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t bars = base + NS * Cfg::STAGE_BYTES;
     const int tid = threadIdx.x;
-    const unsigned n_items = (unsigned)tiles_x * tiles_y * zchunks;
 
     if (tid == 0) {
         tma::prefetch_map(&cur_map);
@@ -342,20 +338,13 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
     // byte offset of this thread's centre pair inside a stage (row rr: + 4 rr BOXX 8)
     const uint32_t so = (uint32_t)(((ty + 1) * BOXX + 2 * tx + Cfg::HX) * 8);
 
-    // planes are numbered consecutively over the whole life of the CTA: plane number
-    // s lives in stage s % NS and completes phase (s / NS) & 1 of that stage's barrier
-    unsigned seq = 0;
+    // plane number s of this CTA lives in stage s % NS and completes phase
+    // (s / NS) & 1 of that stage's barrier
+    const unsigned seq = 0;
     int bad = 0;
-    unsigned item = PERSIST ? 0u : blockIdx.x;
-    for (;;) {
-        if (PERSIST) {
-            if (tid == 0) s_item = atomicAdd(work_counter, 1u);
-            __syncthreads();  // publishes s_item; also: every thread is done with all stages
-            item = s_item;
-            if (item >= n_items) break;
-        } else {
-            __syncthreads();  // barrier init visible
-        }
+    const unsigned item = blockIdx.x;
+    __syncthreads();  // barrier init visible
+    {
         const int tile_x = (int)(item % (unsigned)tiles_x);
         const int tile_y = (int)((item / (unsigned)tiles_x) % (unsigned)tiles_y);
         const int chunk = (int)(item / ((unsigned)tiles_x * (unsigned)tiles_y));
@@ -463,8 +452,6 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
                 ph_a ^= 1u;
             }
         }
-        seq += (unsigned)n_planes;
-        if (!PERSIST) break;
     }
     raise_flags(bad, flag);
 }
@@ -659,30 +646,6 @@ wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList
     } else {
         const uint32_t t = (b - nb1 - nb2) * THREADS + threadIdx.x;
         if (t < L3.n) bad = boundary_node<3>(cur, prev, L3, t, coeffs, g, courant, courant_sq);
-    }
-    raise_flags(bad, flag);
-}
-
-// The same work as a grid-stride loop over the concatenated lists, for a grid of
-// a few CTAs per SM that stays resident for the whole step: launched BEFORE the air
-// kernel it takes one small slice of every SM's registers, the air kernel's CTAs
-// fill the rest, and the latency-bound boundary walk hides behind the
-// bandwidth-bound stencil instead of running after it.
-template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-wg_boundary_strided(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
-                    BList L3, const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g,
-                    double courant, double courant_sq, int* __restrict__ flag) {
-    int bad = 0;
-    const uint32_t total = L1.n + L2.n + L3.n;
-    for (uint32_t t = blockIdx.x * THREADS + threadIdx.x; t < total; t += gridDim.x * THREADS) {
-        if (t < L1.n) {
-            bad |= boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
-        } else if (t < L1.n + L2.n) {
-            bad |= boundary_node<2>(cur, prev, L2, t - L1.n, coeffs, g, courant, courant_sq);
-        } else {
-            bad |= boundary_node<3>(cur, prev, L3, t - L1.n - L2.n, coeffs, g, courant, courant_sq);
-        }
     }
     raise_flags(bad, flag);
 }
