@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    # the product library is built in-tree (nvcc cross-compiles without a GPU); a fresh
+    # clone has none yet. The oracle builds itself on first use (oracle/wgo.py, rto.py).
+    from wayverb_b200 import build as wvb_build
+    wvb_build.build_lib(force=False)
 
 
 @pytest.fixture(scope="session")
