@@ -26,6 +26,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <experimental/optional>
+#include <random>
+#include <type_traits>
 #include <cstring>
 #include <iterator>
 #include <stdexcept>
@@ -165,55 +168,6 @@ struct run_info final {
 };
 }  // namespace detail
 
-namespace reflection_processor {
-
-/// Device-resident stochastic histogram. Same constructor arguments as
-/// make_stochastic_histogram / make_directional_histogram
-/// (stochastic_histogram.h:176-229): (total_rays, max_image_source_order,
-/// receiver_radius, histogram_sample_rate).
-template <bool Directional>
-class make_device_histogram final {
-public:
-    make_device_histogram(size_t total_rays, size_t max_image_source_order, float receiver_radius,
-                          float histogram_sample_rate)
-            : total_rays_{total_rays}
-            , max_image_source_order_{max_image_source_order}
-            , receiver_radius_{receiver_radius}
-            , histogram_sample_rate_{histogram_sample_rate} {}
-
-    static constexpr bool device_histogram = true;
-    static constexpr bool directional = Directional;
-    size_t total_rays_;
-    size_t max_image_source_order_;
-    float receiver_radius_;
-    float histogram_sample_rate_;
-};
-using make_stochastic_histogram = make_device_histogram<false>;
-using make_directional_histogram = make_device_histogram<true>;
-
-/// visual.h:18-25: keeps the first `items` rays' reflections of every step.
-class make_visual final {
-public:
-    explicit make_visual(size_t items) : items_{items} {}
-    static constexpr bool device_histogram = false;
-    size_t items_;
-    size_t steps_required(size_t depth) const { return depth; }
-    using result_type = util::aligned::vector<util::aligned::vector<reflection>>;
-};
-
-/// Collects {triangle, receiver_visible, keep_going} of the first `max_order`
-/// steps for every ray: the input of the image-source path builder
-/// (image_source/reflection_path_builder.h:15-24), which stays host code.
-class make_first_reflections final {
-public:
-    explicit make_first_reflections(size_t max_order) : max_order_{max_order} {}
-    static constexpr bool device_histogram = false;
-    size_t max_order_;
-    using result_type = util::aligned::vector<util::aligned::vector<reflection>>;  // [step][ray]
-};
-
-}  // namespace reflection_processor
-
 namespace detail {
 inline stochastic::energy_histogram to_energy_histogram(const std::vector<double>& h, size_t bins,
                                                         double rate) {
@@ -334,6 +288,336 @@ results run(It b_direction, It e_direction, const core::compute_context& cc,
     }
     ret.completed = true;
     return ret;
+}
+
+// =====================================================================================
+// The reference's own signature: run(b, e, cc, voxelised, source, receiver, environment,
+// keep_going, per_step_callback, callbacks) -> optional<tuple<results...>>
+// (raytracer.h:188-266) with the tuple-of-processors protocol (:51-55,211-243):
+//   callbacks[k].get_processor(cc, source, receiver, environment, voxelised)
+//   processor.get_group_processor(num_directions)
+//   group.process(begin, end, buffers, step, total)     // once per step per segment
+//   processor.accumulate(group)                          // once per segment
+//   processor.get_results()
+// Host processors written against the reference (image source, visual, ...) work
+// unchanged: after a segment has been traced on the device they are fed the
+// `reflection`s of each step they ask for. A processor may declare
+// `size_t steps_required(size_t depth) const` to bound what is copied back (the
+// reference's image-source processor only uses step < max_order, visual every
+// step). Processors that mark themselves `device_resident` (the stochastic
+// histograms below) are evaluated inside the trace kernel instead.
+// =====================================================================================
+}  // namespace raytracer
+
+namespace core {
+/// Stands in for core::scene_buffers (spatial_division/scene_buffers.h:11-60) in the
+/// processors' `process(b, e, buffers, step, total)` signature.
+struct scene_buffers final {
+    wvb_rt* handle;
+};
+}  // namespace core
+
+namespace raytracer {
+namespace reflection_processor {
+
+/// Device-resident stochastic histogram following the processor protocol; same
+/// constructor arguments as the reference's make_stochastic_histogram /
+/// make_directional_histogram (stochastic_histogram.h:176-229).
+template <bool Directional>
+class device_histogram_processor final {
+public:
+    static constexpr bool device_resident = true;
+    static constexpr bool directional = Directional;
+    using result_type = typename std::conditional<Directional, stochastic::directional_energy_histogram<20, 9>,
+                                                  stochastic::energy_histogram>::type;
+    device_histogram_processor(size_t total_rays, size_t max_image_source_order, float receiver_radius,
+                               float histogram_sample_rate)
+            : total_rays{total_rays}
+            , max_image_source_order{max_image_source_order}
+            , receiver_radius{receiver_radius}
+            , histogram_sample_rate{histogram_sample_rate} {}
+    struct group final {
+        template <typename It>
+        void process(It, It, const core::scene_buffers&, size_t, size_t) {}
+    };
+    group get_group_processor(size_t) const { return {}; }
+    void accumulate(const group&) {}
+    result_type get_results() const { return results; }
+
+    size_t total_rays, max_image_source_order;
+    float receiver_radius, histogram_sample_rate;
+    result_type results{};
+};
+
+template <bool Directional>
+class make_histogram final {  // see the aliases below
+public:
+    make_histogram(size_t total_rays, size_t max_image_source_order, float receiver_radius,
+                   float histogram_sample_rate)
+            : p_{total_rays, max_image_source_order, receiver_radius, histogram_sample_rate} {}
+    template <typename Scene>
+    device_histogram_processor<Directional> get_processor(const core::compute_context&, const core::vec3&,
+                                                          const core::vec3&, const core::environment&,
+                                                          const Scene&) const {
+        return p_;
+    }
+
+private:
+    device_histogram_processor<Directional> p_;
+};
+
+using make_stochastic_histogram = make_histogram<false>;
+using make_directional_histogram = make_histogram<true>;
+
+/// visual.h:18-71 restated on the protocol: the first `items` reflections of every
+/// step, from the first segment only (visual.cpp accumulate keeps the first).
+class visual_group_processor final {
+public:
+    explicit visual_group_processor(size_t items) : items_{items} {}
+    template <typename It>
+    void process(It b, It e, const core::scene_buffers&, size_t, size_t) {
+        const size_t n = std::min<size_t>(items_, size_t(std::distance(b, e)));
+        data_.emplace_back(b, b + n);
+    }
+    const util::aligned::vector<util::aligned::vector<reflection>>& get_results() const { return data_; }
+
+private:
+    size_t items_;
+    util::aligned::vector<util::aligned::vector<reflection>> data_;  // [step][item]
+};
+class visual_processor final {
+public:
+    explicit visual_processor(size_t items) : items_{items} {}
+    visual_group_processor get_group_processor(size_t) const { return visual_group_processor{items_}; }
+    void accumulate(const visual_group_processor& g) {
+        if (results_.empty()) results_ = g.get_results();
+    }
+    util::aligned::vector<util::aligned::vector<reflection>> get_results() const { return results_; }
+
+private:
+    size_t items_;
+    util::aligned::vector<util::aligned::vector<reflection>> results_;
+};
+class make_visual final {
+public:
+    explicit make_visual(size_t items) : items_{items} {}
+    template <typename Scene>
+    visual_processor get_processor(const core::compute_context&, const core::vec3&, const core::vec3&,
+                                   const core::environment&, const Scene&) const {
+        return visual_processor{items_};
+    }
+
+private:
+    size_t items_;
+};
+
+/// The input of the image-source model (reflection_processor/image_source.h:17-26 pushes
+/// the reflections of steps < max_order into reflection_path_builder): per ray, the
+/// reflections of its first max_order steps. The path tree / validation stays host code.
+class first_reflections_group_processor final {
+public:
+    first_reflections_group_processor(size_t max_order, size_t items) : max_order_{max_order}, paths_(items) {}
+    size_t steps_required(size_t depth) const { return std::min(max_order_, depth); }
+    template <typename It>
+    void process(It b, It e, const core::scene_buffers&, size_t step, size_t) {
+        if (step < max_order_) {
+            size_t i = 0;
+            for (auto it = b; it != e; ++it, ++i) paths_[i].push_back(*it);
+        }
+    }
+    const util::aligned::vector<util::aligned::vector<reflection>>& get_results() const { return paths_; }
+
+private:
+    size_t max_order_;
+    util::aligned::vector<util::aligned::vector<reflection>> paths_;  // [ray][step]
+};
+class first_reflections_processor final {
+public:
+    explicit first_reflections_processor(size_t max_order) : max_order_{max_order} {}
+    size_t steps_required(size_t depth) const { return std::min(max_order_, depth); }
+    first_reflections_group_processor get_group_processor(size_t n) const { return {max_order_, n}; }
+    void accumulate(const first_reflections_group_processor& g) {
+        results_.insert(results_.end(), g.get_results().begin(), g.get_results().end());
+    }
+    util::aligned::vector<util::aligned::vector<reflection>> get_results() const { return results_; }
+
+private:
+    size_t max_order_;
+    util::aligned::vector<util::aligned::vector<reflection>> results_;
+};
+class make_image_source_input final {
+public:
+    explicit make_image_source_input(size_t max_order) : max_order_{max_order} {}
+    template <typename Scene>
+    first_reflections_processor get_processor(const core::compute_context&, const core::vec3&,
+                                              const core::vec3&, const core::environment&,
+                                              const Scene&) const {
+        return first_reflections_processor{max_order_};
+    }
+
+private:
+    size_t max_order_;
+};
+
+}  // namespace reflection_processor
+
+namespace detail {
+
+template <typename T, typename = void>
+struct is_device_resident : std::false_type {};
+template <typename T>
+struct is_device_resident<T, typename std::enable_if<T::device_resident>::type> : std::true_type {};
+
+template <typename T>
+auto steps_required_of(const T& t, size_t depth, int) -> decltype(t.steps_required(depth)) {
+    return t.steps_required(depth);
+}
+template <typename T>
+size_t steps_required_of(const T&, size_t depth, long) {
+    return depth;
+}
+
+template <typename Tuple, typename F, size_t... Ix>
+void for_each_in(Tuple& t, F&& f, std::index_sequence<Ix...>) {
+    using expand = int[];
+    (void)expand{0, ((void)f(std::get<Ix>(t), std::integral_constant<size_t, Ix>{}), 0)...};
+}
+template <typename... Ts, typename F>
+void for_each_in(std::tuple<Ts...>& t, F&& f) {
+    for_each_in(t, std::forward<F>(f), std::index_sequence_for<Ts...>{});
+}
+
+// device-histogram parameters found among the processors (at most one is honoured)
+struct histogram_request final {
+    bool present{false};
+    bool directional{false};
+    size_t max_order{0};
+    float radius{0.1f};
+    float rate{1000.0f};
+};
+template <bool D>
+void note_histogram(const reflection_processor::device_histogram_processor<D>& p, histogram_request& r) {
+    if (!r.present) r = {true, D, p.max_image_source_order, p.receiver_radius, p.histogram_sample_rate};
+}
+template <typename T>
+void note_histogram(const T&, histogram_request&) {}
+
+inline void store_histogram(reflection_processor::device_histogram_processor<false>& p,
+                            const std::vector<double>& h, size_t bins) {
+    p.results = to_energy_histogram(h, bins, p.histogram_sample_rate);
+}
+inline void store_histogram(reflection_processor::device_histogram_processor<true>& p,
+                            const std::vector<double>& h, size_t bins) {
+    p.results.sample_rate = p.histogram_sample_rate;
+    for (size_t a = 0; a < 20; ++a) {
+        for (size_t e = 0; e < 9; ++e) {
+            std::vector<double> cell(h.begin() + (a * 9 + e) * bins * 8, h.begin() + (a * 9 + e + 1) * bins * 8);
+            p.results.histogram.table[a][e] = to_energy_histogram(cell, bins, p.histogram_sample_rate).histogram;
+        }
+    }
+}
+template <typename T>
+void store_histogram(T&, const std::vector<double>&, size_t) {}
+
+}  // namespace detail
+
+namespace detail {
+template <typename Tuple, size_t... Ix>
+auto make_processors(Tuple& cbs, std::index_sequence<Ix...>, const core::compute_context& cc,
+                     const core::vec3& source, const core::vec3& receiver, const core::environment& env,
+                     const core::flattened_scene& scene) {
+    return std::make_tuple(std::get<Ix>(cbs).get_processor(cc, source, receiver, env, scene)...);
+}
+template <typename Tuple, size_t... Ix>
+auto collect_results(Tuple& procs, std::index_sequence<Ix...>) {
+    return std::make_tuple(std::get<Ix>(procs).get_results()...);
+}
+}  // namespace detail
+
+template <typename It, typename PerStepCallback, typename... Callbacks>
+auto run(It b_direction, It e_direction, const core::compute_context& cc,
+         const core::flattened_scene& voxelised, const core::vec3& source, const core::vec3& receiver,
+         const core::environment& environment, const std::atomic_bool& keep_going,
+         PerStepCallback&& per_step_callback, std::tuple<Callbacks...> callbacks,
+         uint64_t seed = std::random_device{}()) {
+    const detail::scene_handle h{cc, voxelised};
+    const core::scene_buffers buffers{h.get()};
+    const auto seq = std::index_sequence_for<Callbacks...>{};
+
+    auto processors = detail::make_processors(callbacks, seq, cc, source, receiver, environment, voxelised);
+    using return_type = decltype(detail::collect_results(processors, seq));
+
+    const size_t total = size_t(std::distance(b_direction, e_direction));
+    constexpr size_t segment_size = 1 << 14;                               // raytracer.h:219
+    const size_t depth = compute_optimum_reflection_number(voxelised);     // :220-221
+
+    detail::histogram_request hist;
+    size_t keep = 0;
+    detail::for_each_in(processors, [&](auto& p, auto) {
+        detail::note_histogram(p, hist);
+        if (!detail::is_device_resident<std::decay_t<decltype(p)>>::value) {
+            keep = std::max(keep, detail::steps_required_of(p, depth, 0));
+        }
+    });
+
+    wvb_rt_trace_params p{};
+    p.source[0] = source.x; p.source[1] = source.y; p.source[2] = source.z;
+    p.receiver[0] = receiver.x; p.receiver[1] = receiver.y; p.receiver[2] = receiver.z;
+    p.receiver_radius = hist.radius;
+    p.speed_of_sound = environment.speed_of_sound;
+    p.histogram_sample_rate = hist.rate;
+    p.total_rays = total;
+    p.seed = seed;
+    p.depth = uint32_t(depth);
+    p.specular_from_step = uint32_t(hist.max_order);  // stochastic_histogram.h:98-101
+    p.n_bins = hist.present ? wvb_rt_safe_bins(h.get(), p.depth, p.speed_of_sound, p.histogram_sample_rate) : 1;
+    p.directional = hist.directional ? 1 : 0;
+    p.keep_steps = uint32_t(keep);
+    core::detail::check(wvb_rt_reset_histogram(h.get()));
+
+    std::vector<float> dirs;
+    std::vector<reflection> refl;
+    const auto run_segment = [&](It b, size_t n, size_t base) {
+        dirs.resize(n * 3);
+        auto it = b;
+        for (size_t i = 0; i < n; ++i, ++it) {
+            const auto d = *it;
+            dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z;
+        }
+        refl.resize(keep * n);
+        p.ray_index_base = base;
+        core::detail::check(wvb_rt_trace(h.get(), &p, dirs.data(), n,
+                                         keep ? reinterpret_cast<wvb_reflection*>(refl.data()) : nullptr,
+                                         nullptr, nullptr));
+        detail::for_each_in(processors, [&](auto& proc, auto) {
+            auto group = proc.get_group_processor(n);
+            if (!detail::is_device_resident<std::decay_t<decltype(proc)>>::value) {
+                const size_t steps = std::min(keep, detail::steps_required_of(proc, depth, 0));
+                for (size_t s = 0; s < steps; ++s) {
+                    group.process(refl.begin() + s * n, refl.begin() + (s + 1) * n, buffers, s, depth);
+                }
+            }
+            proc.accumulate(group);
+        });
+    };
+
+    const size_t groups = total / segment_size;
+    size_t done = 0, group = 0;
+    auto it = b_direction;
+    for (; done + segment_size <= total; done += segment_size, ++group) {
+        run_segment(it, segment_size, done);
+        std::advance(it, segment_size);
+        per_step_callback(group, groups);
+        if (!keep_going) return std::experimental::optional<return_type>{};
+    }
+    if (done != total) run_segment(it, total - done, done);
+
+    if (hist.present) {
+        std::vector<double> hbuf(size_t(p.n_bins) * 8 * (hist.directional ? 180 : 1));
+        core::detail::check(wvb_rt_read_histogram(h.get(), hbuf.data()));
+        detail::for_each_in(processors, [&](auto& proc, auto) { detail::store_histogram(proc, hbuf, p.n_bins); });
+    }
+    return std::experimental::make_optional(detail::collect_results(processors, seq));
 }
 
 }  // namespace raytracer

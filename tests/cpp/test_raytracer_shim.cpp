@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <tuple>
 #include <random>
 #include <vector>
 
@@ -89,6 +91,35 @@ int main() {
     auto partial = raytracer::run(dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{},
                                   stop, [&](auto, auto) { ++seen; }, 4, 0.1f, 1000.0f, false, 0, 1);
     if (partial.completed || seen != 1) return 10;
+    // the reference's own signature: a tuple of callbacks -> optional<tuple<results...>>
+    // (canonical.cpp:9-20: image-source input + directional histogram + visual)
+    {
+        int steps_seen = 0;
+        auto tup = raytracer::run(
+                dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{}, true,
+                [&](auto, auto) { ++steps_seen; },
+                std::make_tuple(raytracer::reflection_processor::make_image_source_input{4},
+                                raytracer::reflection_processor::make_stochastic_histogram{rays, 4 + 1, 0.1f, 1000.0f},
+                                raytracer::reflection_processor::make_visual{32}),
+                1234);
+        if (!tup || steps_seen != 2) return 11;
+        const auto& paths = std::get<0>(*tup);
+        const auto& hist = std::get<1>(*tup);
+        const auto& visual = std::get<2>(*tup);
+        if (paths.size() != rays || paths[0].size() != 4) return 12;
+        if (visual.size() != 132 || visual[0].size() != 32) return 13;  // no bound declared: every step
+        // same seed, same directions, same gate (order + 1) as the explicit-parameter run above
+        if (hist.histogram.size() != res.histogram.histogram.size()) return 14;
+        for (size_t b = 0; b < hist.histogram.size(); ++b) {
+            for (int k = 0; k < 8; ++k) {
+                const float x = hist.histogram[b].s[k], y = res.histogram.histogram[b].s[k];
+                if (std::fabs(x - y) > 1e-6f * std::fabs(y) + 1e-30f) return 15;
+            }
+        }
+        for (size_t i = 0; i < rays; i += 997) {
+            if (std::memcmp(&paths[i][0], &res.first_reflections[0][i], sizeof(raytracer::reflection))) return 16;
+        }
+    }
     std::printf("RT_SHIM_OK energy=%g bins=%zu\n", total, res.histogram.histogram.size());
     return 0;
 }
