@@ -1,0 +1,38 @@
+"""A/B of two builds of libwvb200.so on the SAME box (boxes differ by ~8 %):
+alternates the libraries in fresh processes and prints the step time of each.
+usage: ab_lib.py libA.so libB.so [rounds]"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+import wayverb_b200 as wvb
+from wayverb_b200 import _lib
+s = json.load(open(%r))["sets"][0]["impedance"]
+c = np.zeros((), _lib.COEFF_DT); c["b"], c["a"] = s["b"], s["a"]
+m = wvb.cuboid_mesh((512, 512, 512), [c])
+with wvb.Waveguide(m) as g:
+    g.write(m.index(256, 256, 256), 1.0)
+    g.time_steps(20)
+    best = min(g.time_steps(100)[0] for _ in range(3)) / 100
+    k = g.time_kernels(100)
+    print(json.dumps({"step_ms": best, "air_ms": k[0] / 100, "bnd_ms": k[1] / 100}))
+''' % (ROOT, os.path.join(ROOT, "tests", "golden", "lrs_coefficients.json"))
+
+
+def main():
+    libs = sys.argv[1:3]
+    rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    for r in range(rounds):
+        for lib in libs:
+            env = dict(os.environ, WVB_LIB=os.path.abspath(lib))
+            out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
+            print(r, os.path.basename(lib), out.stdout.strip() or out.stderr[-300:], flush=True)
+
+
+if __name__ == "__main__":
+    main()
