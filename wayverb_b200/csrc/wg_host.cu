@@ -473,7 +473,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     g.dx = dx; g.dy = dy; g.nzl = d->z_end - d->z_begin;
     g.px = (dx + WG_XO + 2 + 3) & ~3;  // zero border: WG_XO columns left, >= 2 right
     g.py = dy + 2;                     // zero rows above and below
-    g.pc = ((dx + 1 + 3) / 4 + 15) & ~15;  // 2-bit classes, 4 per byte: >= 1 "do not write" column right of the row
+    g.pc = (dx + 1 + 15) & ~15;        // class bytes: >= 1 "do not write" column right of the row
     g.plane = (long long)g.px * g.py;
     g.cplane = (long long)g.pc * dy;
     const long long total = g.plane * (g.nzl + 2);
@@ -481,7 +481,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
 
     // ---- digest the nodes: class bytes + boundary lists (node order) ----------
     const node_view nv{d->nodes, d->nodes_z0, d->nodes_nz, dx, dy, dz};
-    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), (uint8_t)(CLS_BOUNDARY * 0x55));
+    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), CLS_BOUNDARY);
     std::vector<std::array<uint32_t, 3>> plane_counts(g.nzl);
     std::vector<uint64_t> plane_air(g.nzl, 0);
     parallel_for(g.nzl, [&](int64_t lp) {
@@ -493,8 +493,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
             for (int x = 0; x < dx; ++x) {
                 int nd;
                 const int cls = node_class(nv.type_at(x, y, z), &nd);
-                uint8_t& byte = crow[(size_t)y * g.pc + (x >> 2)];
-                byte = (uint8_t)((byte & ~(3u << ((x & 3) * 2))) | ((unsigned)cls << ((x & 3) * 2)));
+                crow[(size_t)y * g.pc + x] = (uint8_t)cls;
                 if (cls == CLS_BOUNDARY) c[nd - 1]++;
                 if (cls == CLS_AIR) air++;
             }

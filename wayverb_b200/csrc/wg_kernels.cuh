@@ -26,9 +26,8 @@
 //          (program.cpp:402-407) needs no bounds test. Node (x, y, local plane
 //          lz) lives at ((lz*(dy+2) + y+1)*px + WG_XO + x); WG_XO = 4 and px a
 //          multiple of 4 keep node pairs 16-byte and rows 32-byte aligned.
-//   code   2-bit node class, four nodes per byte (node x of a row sits in bits
-//          2*(x&3) of byte x>>2), (nzl+2) x dy x pc bytes (no border); columns >= dx
-//          of a row are CLS_BOUNDARY ("do not write").
+//   code   u8 node class, (nzl+2) x dy x pc bytes (no border); columns >= dx of
+//          a row are CLS_BOUNDARY ("do not write").
 //   lists  per boundary class N: off[n] (element offset into P), meta[n],
 //          ci[N][n] coefficient indices, mem[N][6][n] filter memory.
 #pragma once
@@ -125,8 +124,7 @@ __device__ __forceinline__ void raise_flags(int bad, int* flag) {
 // The update of one x-adjacent node pair (normal_waveguide_update,
 // program.cpp:393-412, for both nodes). Port order nx, px, ny, py, nz, pz; the
 // leading `0 +` of the reference is the first operand itself. `ck` holds the two
-// 2-bit classes (node 0 in bits 0-1, node 1 in bits 2-3). Writes the result(s) to
-// dst unless the class says BOUNDARY.
+// class bytes. Writes the result(s) to dst unless the class says BOUNDARY.
 template <bool FAST_DIV>
 __device__ __forceinline__ void update_pair(double l, double2 mid, double r, double2 u, double2 d,
                                             double2 below, double2 above, double2 p, unsigned ck,
@@ -141,7 +139,7 @@ __device__ __forceinline__ void update_pair(double l, double2 mid, double r, dou
         v0 = s0 / 3.0 - p.x;
         v1 = s1 / 3.0 - p.y;
     }
-    const unsigned c0 = ck & 3u, c1 = (ck >> 2) & 3u;
+    const unsigned c0 = ck & 0xffu, c1 = ck >> 8;
     if (c0 != CLS_AIR) v0 = 0.0;
     if (c1 != CLS_AIR) v1 = 0.0;
     if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {  // rare: inf / nan
@@ -180,13 +178,12 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
         const uint32_t row = (uint32_t)g.px;
         const uint32_t ksp = (uint32_t)g.cplane;
         uint32_t off = (uint32_t)wg_offset(g, x0, y, zs);
-        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y) * g.pc + (x0 >> 2));
-        const unsigned kshift = (unsigned)(x0 & 2) << 1;  // this pair's nibble in its class byte
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y) * g.pc + x0);
         int z = zs;
         auto iter = [&](const double2& below, const double2& mid, double2& above) {
             above = ld2(cur + (off + sp));
             const double2 p = ld2(prev + off);
-            const unsigned ck = (unsigned)code[koff] >> kshift;
+            const unsigned ck = *reinterpret_cast<const unsigned short*>(code + koff);
             if (PF > 0 && z + PF <= g.nzl) {
                 prefetch_l2(cur + (off + (PF + 1) * sp));
                 prefetch_l2(prev + (off + PF * sp));
@@ -376,18 +373,17 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) valid[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
         uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, zs);  // row rr: + 4 rr px
-        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + (x >> 2));
-        const unsigned kshift = (unsigned)(x & 2) << 1;  // this pair's nibble in its class byte
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + x);
 
         double2 p_next[R];
         unsigned c_next[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             p_next[rr] = make_double2(0.0, 0.0);
-            c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 2);
+            c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 8);
             if (valid[rr]) {
                 p_next[rr] = ld2(prev + (off + rr * rstep));
-                c_next[rr] = (unsigned)code[koff + rr * krstep] >> kshift;
+                c_next[rr] = *reinterpret_cast<const unsigned short*>(code + (koff + rr * krstep));
             }
         }
 
@@ -418,7 +414,8 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
                 for (int rr = 0; rr < R; ++rr) {
                     if (valid[rr]) {
                         p_next[rr] = ld2(prev + (off + sp + rr * rstep));
-                        c_next[rr] = (unsigned)code[koff + ksp + rr * krstep] >> kshift;
+                        c_next[rr] = *reinterpret_cast<const unsigned short*>(
+                                code + (koff + ksp + rr * krstep));
                     }
                 }
             }
