@@ -1,6 +1,7 @@
 """A/B of two builds of libwvb200.so on the SAME box (boxes differ by ~8 %):
 alternates the libraries in fresh processes and prints the step time of each.
-usage: ab_lib.py libA.so libB.so [rounds]"""
+usage: ab_lib.py A B [C ...] [rounds]   where each arm is a library path or a
+comma-separated list of environment settings (WVB_WG_BPIPE=4,WVB_WG_BMINB=4)."""
 import json
 import os
 import subprocess
@@ -25,11 +26,17 @@ with wvb.Waveguide(m) as g:
 
 
 def main():
-    libs = sys.argv[1:3]
-    rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    args = sys.argv[1:]
+    rounds = 3
+    if args and args[-1].isdigit():
+        rounds = int(args.pop())
     for r in range(rounds):
-        for lib in libs:
-            env = dict(os.environ, WVB_LIB=os.path.abspath(lib))
+        for lib in args:
+            if "=" in lib or lib == "default":
+                env = dict(os.environ)
+                env.update(kv.split("=", 1) for kv in lib.split(",") if "=" in kv)
+            else:
+                env = dict(os.environ, WVB_LIB=os.path.abspath(lib))
             out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
             print(r, os.path.basename(lib), out.stdout.strip() or out.stderr[-300:], flush=True)
 

@@ -94,7 +94,8 @@ struct wvb_wg {
     cudaStream_t stream_b = nullptr;  // boundary kernel runs here, next to the air kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
-    int bminb = 8;
+    int bminb = 4;
+    int bpipe = 4;  // >0: pipelined 1-d boundary walk with this many blocks per SM
     int air_first = 1;
     dev_buf<uint32_t> step_counter;
     int use_graph = 1;
@@ -316,24 +317,31 @@ void launch_air(wvb_wg* w, const double* cur, double* prev) {
     w->launches++;
 }
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool PIPE>
 void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     const uint32_t n1 = w->bl[0].n, n2 = w->bl[1].n, n3 = w->bl[2].n;
     const uint32_t T = THREADS;
-    const uint32_t nb1 = (n1 + T - 1) / T, nb2 = (n2 + T - 1) / T, nb3 = (n3 + T - 1) / T;
+    uint32_t nb1 = (n1 + T - 1) / T;
+    const uint32_t nb2 = (n2 + T - 1) / T, nb3 = (n3 + T - 1) / T;
+    if (PIPE) nb1 = std::min<uint32_t>(nb1, (uint32_t)(w->sm_count * w->bpipe));
     auto L = [&](int k) {
         auto& l = w->bl[k];
         return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
     };
-    wg_boundary_all<THREADS, MINB><<<nb1 + nb2 + nb3, T, 0, st>>>(
+    wg_boundary_all<THREADS, MINB, PIPE><<<nb1 + nb2 + nb3, T, 0, st>>>(
             cur, prev, L(0), L(1), L(2), nb1, nb2, w->coeffs.p, w->g, w->courant, w->courant_sq,
             w->flag.p);
 }
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
-    if (w->bminb >= 8) launch_boundary_t<128, 8>(w, cur, prev, st);
-    else launch_boundary_t<128, 5>(w, cur, prev, st);
+    if (w->bpipe > 0) {
+        if (w->bminb >= 6) launch_boundary_t<128, 6, true>(w, cur, prev, st);
+        else if (w->bminb == 5) launch_boundary_t<128, 5, true>(w, cur, prev, st);
+        else if (w->bminb == 4) launch_boundary_t<128, 4, true>(w, cur, prev, st);
+        else launch_boundary_t<128, 3, true>(w, cur, prev, st);
+    } else if (w->bminb >= 8) launch_boundary_t<128, 8, false>(w, cur, prev, st);
+    else launch_boundary_t<128, 5, false>(w, cur, prev, st);
     w->launches++;
 }
 
@@ -565,7 +573,8 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
-    w->bminb = env_int("WVB_WG_BMINB", 8);
+    w->bminb = env_int("WVB_WG_BMINB", 4);
+    w->bpipe = env_int("WVB_WG_BPIPE", 4);
     w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);

@@ -625,11 +625,111 @@ __global__ void wg_filter_test(const double* __restrict__ biquads /* [stream][3]
     }
 }
 
+// ---------------------------------------------------------------------------
+// Software-pipelined walk of the 1-d list (the bulk of all boundary nodes).
+// One node costs two dependent memory round trips (list entry -> pressures and
+// filter state) and ~600 instructions in between; with one node per thread all
+// warps of an SM sit in the same phase. Here a thread owns nodes t, t+stride, ...:
+// while node j is computed, the pressures/state of node j+1 and the list entry of
+// node j+2 are already in flight. Same arithmetic, same order, as boundary_node<1>.
+// ---------------------------------------------------------------------------
+struct B1Entry {
+    uint32_t off, meta, ci;
+};
+struct B1Data {
+    double inner, s0, s1, s2, s3, prevp;
+    double m[6];
+};
+__device__ __forceinline__ B1Entry b1_load_entry(const BList& L, uint32_t t) {
+    return B1Entry{L.off[t], L.meta[t], L.ci[t]};
+}
+__device__ __forceinline__ B1Data b1_load_data(const double* __restrict__ cur,
+                                               const double* __restrict__ prev, const BList& L,
+                                               uint32_t t, const B1Entry& e, const WgGeom& g) {
+    B1Data d;
+    const double* c = cur + e.off;
+    const uint32_t inmesh = (e.meta >> META_PORTMASK_SHIFT) & 63u;
+    const int port = e.meta & 7u;
+    const bool ok = port >= 6 || ((inmesh >> port) & 1u);
+    d.inner = ok ? c[port_delta(port, g)] : 0.0;
+    d.s0 = d.s1 = d.s2 = d.s3 = 0.0;
+    if (!(e.meta & META_SURROUND_ZERO)) {
+        const int ax = port >> 1;  // on_boundary_1 (program.cpp:112-131)
+        const long long dxp = 1, dyp = g.px, dzp = g.plane;
+        long long a, b;
+        if (ax == 0) { a = dyp; b = dzp; }
+        else if (ax == 1) { a = dxp; b = dzp; }
+        else if (ax == 2) { a = dxp; b = dyp; }
+        else { a = 0; b = 0; }
+        d.s0 = c[-a];
+        d.s1 = c[a];
+        d.s2 = c[-b];
+        d.s3 = c[b];
+    }
+    d.prevp = prev[e.off];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.m[k] = L.mem[(size_t)k * L.n + t];
+    return d;
+}
+__device__ __forceinline__ int b1_compute(double* __restrict__ prev, const BList& L, uint32_t t,
+                                          const B1Entry& e, B1Data& d,
+                                          const wvb_coefficients_canonical* __restrict__ coeffs,
+                                          double courant, double courant_sq) {
+    int bad = 0;
+    if (e.meta & META_ERR_OUTSIDE) bad |= WVB_FLAG_OUTSIDE_MESH;
+    if (e.meta & META_ERR_SUSPICIOUS) bad |= WVB_FLAG_SUSPICIOUS_BOUNDARY;
+    const double sum = 0.0 + 2 * d.inner;
+    double surround = 0.0;
+    surround += d.s0;
+    surround += d.s1;
+    surround += d.s2;
+    surround += d.s3;
+    const double csw = courant_sq * (sum + surround);
+    const wvb_coefficients_canonical c = coeffs[e.ci];
+    const double fsum = 0.0 + d.m[0] / c.b[0];
+    const double fw = courant_sq * fsum;
+    const double csum = 0.0 + c.a[0] / c.b[0];
+    const double cw = csum * courant;
+    const double pw = (cw - 1) * d.prevp;
+    const double ret = (csw + fw + pw) / (1 + cw);
+    const double diff = (c.a[0] * (d.prevp - ret)) / (c.b[0] * courant) + (d.m[0] / c.b[0]);
+    filter_step_6(-diff, d.m, c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) L.mem[(size_t)k * L.n + t] = d.m[k];
+    bad |= classify_bad(ret);
+    prev[e.off] = ret;
+    return bad;
+}
+__device__ __forceinline__ int boundary_1d_pipelined(
+        const double* __restrict__ cur, double* __restrict__ prev, const BList& L, uint32_t t,
+        uint32_t stride, const wvb_coefficients_canonical* __restrict__ coeffs, const WgGeom& g,
+        double courant, double courant_sq) {
+    int bad = 0;
+    if (t >= L.n) return 0;
+    B1Entry e0 = b1_load_entry(L, t), e1 = e0;
+    if (t + stride < L.n) e1 = b1_load_entry(L, t + stride);
+    B1Data d0 = b1_load_data(cur, prev, L, t, e0, g), d1 = d0;
+    while (true) {
+        const uint32_t t1 = t + stride, t2 = t1 + stride;
+        const bool more = t1 < L.n;
+        B1Entry e2 = e1;
+        if (more) d1 = b1_load_data(cur, prev, L, t1, e1, g);
+        if (t2 < L.n) e2 = b1_load_entry(L, t2);
+        bad |= b1_compute(prev, L, t, e0, d0, coeffs, courant, courant_sq);
+        if (!more) break;
+        e0 = e1;
+        d0 = d1;
+        e1 = e2;
+        t = t1;
+    }
+    return bad;
+}
+
 // All three boundary classes in one launch: blocks [0, nb1) walk the 1-d list,
 // [nb1, nb1 + nb2) the 2-d list, the rest the 3-d list. Runs on its own stream
 // next to the air-node kernel: the two touch disjoint nodes of `prev` and only
 // read `cur`.
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool PIPE>
 __global__ void __launch_bounds__(THREADS, MINB)
 wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
                 BList L3, uint32_t nb1, uint32_t nb2,
@@ -639,7 +739,12 @@ wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList
     const uint32_t b = blockIdx.x;
     if (b < nb1) {
         const uint32_t t = b * THREADS + threadIdx.x;
-        if (t < L1.n) bad = boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
+        if (PIPE) {  // nb1 blocks stride over the whole list
+            bad = boundary_1d_pipelined(cur, prev, L1, t, nb1 * THREADS, coeffs, g, courant,
+                                        courant_sq);
+        } else if (t < L1.n) {
+            bad = boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
+        }
     } else if (b < nb1 + nb2) {
         const uint32_t t = (b - nb1) * THREADS + threadIdx.x;
         if (t < L2.n) bad = boundary_node<2>(cur, prev, L2, t, coeffs, g, courant, courant_sq);
