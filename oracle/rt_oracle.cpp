@@ -20,6 +20,7 @@
 //                                  src/raytracer/src/stochastic/finder.cpp:7-15
 //   segment/depth loop             src/raytracer/include/raytracer/raytracer.h:188-266
 //   histogram binning              src/raytracer/include/raytracer/reflection_processor/stochastic_histogram.h:17-32,70-111
+//   image-source stage             see is_oracle.inc (included at the end)
 //   direction -> LUT cell          src/core/include/core/vector_look_up_table.h:53-116, src/core/src/az_el.cpp:53-68
 //
 // All ray arithmetic is fp32 in the reference and here; operation order is
@@ -776,3 +777,5 @@ int rto_num_threads() {
 size_t rto_params_size() { return sizeof(trace_params); }
 
 }  // extern "C"
+
+#include "is_oracle.inc"

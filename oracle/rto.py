@@ -30,8 +30,8 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "rt_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("rt_oracle.cpp", "is_oracle.inc")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.run(["make", "-C", _HERE, "_build/librtoracle.so"], check=True, stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -54,6 +54,10 @@ def lib():
         L.rto_nodes_inside.argtypes = [vp, vp, vp, C.c_float, vp]
         L.rto_closest_surface.argtypes = [vp, vp, sz, vp, vp]
         L.rto_trace.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+        L.rto_image_source.restype = sz
+        L.rto_image_source.argtypes = [vp, vp, vp, vp, sz, sz, C.c_double, C.c_int, C.c_int, vp, sz, vp]
+        L.rto_exact_shoebox.restype = sz
+        L.rto_exact_shoebox.argtypes = [vp, vp, vp, vp, C.c_float, C.c_double, C.c_double, vp, sz]
         L.rto_num_threads.restype = C.c_int
         L.rto_params_size.restype = sz
         assert L.rto_params_size() == C.sizeof(TraceParams)
@@ -128,6 +132,50 @@ class Scene:
         lib().rto_trace(self._h, C.byref(P), _p(d), n, _p(hist), C.byref(dropped),
                         _p(refl) if refl is not None else None)
         return hist, refl, dropped.value
+
+
+IMPULSE_DT = np.dtype([("volume", np.float32, 8), ("position", np.float32, 4), ("distance", np.float32),
+                       ("pad_", np.float32, 3)])  # raytracer::impulse<8>, 64 B
+IS_NONE = 0xFFFFFFFF
+IS_VISIBLE = 0x80000000
+
+
+def path_elements(refl, order):
+    """reflection records [steps][n] -> image-source path elements [order][n]
+    (reflection_path_builder.h:16-26, group processor: step < max_order)."""
+    k = min(order, refl.shape[0])
+    tri = refl["triangle"][:k].astype(np.uint32)
+    e = np.where(refl["keep_going"][:k] != 0,
+                 tri | np.where(refl["receiver_visible"][:k] != 0, np.uint32(IS_VISIBLE), np.uint32(0)),
+                 np.uint32(IS_NONE)).astype(np.uint32)
+    return np.ascontiguousarray(e)
+
+
+def image_source(scene, elems, source, receiver, acoustic_impedance=400.0, flip_phase=False, with_direct=True):
+    """the reference's image-source stage on path elements [order][n_rays] -> (impulses, stats)"""
+    e = np.ascontiguousarray(elems, np.uint32)
+    order, n = e.shape
+    s = np.asarray(source, np.float32)
+    r = np.asarray(receiver, np.float32)
+    stats = np.zeros(3, np.uint64)
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, IMPULSE_DT)
+        cnt = lib().rto_image_source(scene._h, _p(s), _p(r), _p(e), n, order, float(acoustic_impedance),
+                                     int(flip_phase), int(with_direct), _p(out), cap, _p(stats))
+        if cnt <= cap:
+            return out[:cnt], stats
+        cap = cnt
+
+
+def exact_shoebox(box_min, box_max, source, receiver, absorption, max_distance, acoustic_impedance=400.0):
+    a = [np.asarray(v, np.float32) for v in (box_min, box_max, source, receiver)]
+    cap = 1 << 16
+    out = np.zeros(cap, IMPULSE_DT)
+    n = lib().rto_exact_shoebox(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), float(absorption), float(max_distance),
+                                float(acoustic_impedance), _p(out), cap)
+    assert n <= cap
+    return out[:n]
 
 
 def ray_energy(total_rays, source, receiver, radius):

@@ -29,6 +29,7 @@ struct wvb_rt {
     dev_buf<rt::VoxEntry> entries;
     dev_buf<double> hist;
     dev_buf<unsigned long long> dropped;
+    dev_buf<float> dirs;
     rt::Scene sc{};
     uint32_t hist_bins = 0, hist_directional = 0;
     float diag = 0;
@@ -77,6 +78,53 @@ float ray_energy(uint64_t total_rays, const float* s, const float* r, float radi
 const rt::Scene* wvb_rt_device_scene(const wvb_rt* r, int* device) {
     if (device) *device = r->dev;
     return &r->sc;
+}
+
+cudaStream_t wvb_rt_stream(const wvb_rt* r) { return r->stream; }
+
+// Enqueues one trace of n rays on the handle's stream (no synchronisation):
+// directions from the host or generated, the rt_trace launch bracketed by the
+// handle's events, reflections of steps < keep into d_refl (device, [keep][n]).
+// Shared by wvb_rt_trace and the image-source stage (is_host.cu).
+void wvb_rt_trace_enqueue(wvb_rt* r, const wvb_rt_trace_params* p, const float* directions, uint32_t n,
+                          rt::ReflectionPod* d_refl, uint32_t keep) {
+    WVB_REQUIRE(p->n_bins > 0, WVB_ERR_INVALID, "n_bins == 0");
+    WVB_CUDA(cudaSetDevice(r->dev));
+    if (r->hist_bins != p->n_bins || r->hist_directional != (p->directional ? 1u : 0u)) {
+        r->hist.alloc(hist_size(p->n_bins, p->directional), true);
+        r->hist_bins = p->n_bins;
+        r->hist_directional = p->directional ? 1u : 0u;
+        WVB_CUDA(cudaMemsetAsync(r->dropped.p, 0, 8, r->stream));
+    }
+    rt::Params P{};
+    P.source = {p->source[0], p->source[1], p->source[2]};
+    P.receiver = {p->receiver[0], p->receiver[1], p->receiver[2]};
+    P.receiver_radius = p->receiver_radius;
+    P.ray_energy = ray_energy(p->total_rays, p->source, p->receiver, p->receiver_radius);
+    P.speed_of_sound = p->speed_of_sound;
+    P.histogram_rate = p->histogram_sample_rate;
+    P.seed = p->seed;
+    P.ray_index_base = p->ray_index_base;
+    P.depth = p->depth;
+    P.specular_from_step = p->specular_from_step;
+    P.n_bins = p->n_bins;
+    P.directional = p->directional ? 1u : 0u;
+    P.keep_steps = d_refl ? keep : 0u;
+    if (!n) return;
+    // kept in the handle: the kernel runs after we return
+    if (r->dirs.n < (size_t)n * 3) r->dirs.alloc((size_t)n * 3, false);
+    if (directions) {
+        WVB_CUDA(cudaMemcpyAsync(r->dirs.p, directions, (size_t)n * 12, cudaMemcpyHostToDevice, r->stream));
+    } else {
+        rt::rt_directions<<<(n + 255) / 256, 256, 0, r->stream>>>(p->seed, p->ray_index_base, n, r->dirs.p);
+        r->launches++;
+    }
+    WVB_CUDA(cudaEventRecord(r->ev0, r->stream));
+    rt::rt_trace<<<(n + 127) / 128, 128, 0, r->stream>>>(r->sc, P, r->dirs.p, n, r->hist.p, r->dropped.p,
+                                                         P.keep_steps ? d_refl : nullptr);
+    r->launches++;
+    WVB_CUDA(cudaEventRecord(r->ev1, r->stream));
+    WVB_CUDA(cudaGetLastError());
 }
 
 extern "C" {
@@ -198,54 +246,15 @@ wvb_status wvb_rt_trace(wvb_rt* r, const wvb_rt_trace_params* p, const float* di
     if (!r || !p) return WVB_ERR_INVALID;
     return guarded([&] {
         WVB_REQUIRE(n_rays < 0xffffffffull, WVB_ERR_UNSUPPORTED, "too many rays in one call");
-        WVB_REQUIRE(p->n_bins > 0, WVB_ERR_INVALID, "n_bins == 0");
-        WVB_REQUIRE(!(p->keep_steps && !reflections) || true, WVB_ERR_INVALID, "");
-        WVB_CUDA(cudaSetDevice(r->dev));
         const uint32_t n = (uint32_t)n_rays;
-        if (r->hist_bins != p->n_bins || r->hist_directional != (p->directional ? 1u : 0u)) {
-            r->hist.alloc(hist_size(p->n_bins, p->directional), true);
-            r->hist_bins = p->n_bins;
-            r->hist_directional = p->directional ? 1u : 0u;
-            WVB_CUDA(cudaMemsetAsync(r->dropped.p, 0, 8, r->stream));
-        }
-        rt::Params P{};
-        P.source = {p->source[0], p->source[1], p->source[2]};
-        P.receiver = {p->receiver[0], p->receiver[1], p->receiver[2]};
-        P.receiver_radius = p->receiver_radius;
-        P.ray_energy = ray_energy(p->total_rays, p->source, p->receiver, p->receiver_radius);
-        P.speed_of_sound = p->speed_of_sound;
-        P.histogram_rate = p->histogram_sample_rate;
-        P.seed = p->seed;
-        P.ray_index_base = p->ray_index_base;
-        P.depth = p->depth;
-        P.specular_from_step = p->specular_from_step;
-        P.n_bins = p->n_bins;
-        P.directional = p->directional ? 1u : 0u;
-        P.keep_steps = reflections ? p->keep_steps : 0u;
-
-        dev_buf<float> d_dirs;
+        const uint32_t keep = reflections ? p->keep_steps : 0u;
         dev_buf<rt::ReflectionPod> d_refl;
-        if (n) {
-            d_dirs.alloc((size_t)n * 3, false);
-            if (directions) {
-                WVB_CUDA(cudaMemcpyAsync(d_dirs.p, directions, (size_t)n * 12, cudaMemcpyHostToDevice,
-                                         r->stream));
-            } else {
-                rt::rt_directions<<<(n + 255) / 256, 256, 0, r->stream>>>(p->seed, p->ray_index_base, n,
-                                                                          d_dirs.p);
-                r->launches++;
-            }
-            if (P.keep_steps) d_refl.alloc((size_t)P.keep_steps * n, false);
-            WVB_CUDA(cudaEventRecord(r->ev0, r->stream));
-            rt::rt_trace<<<(n + 127) / 128, 128, 0, r->stream>>>(r->sc, P, d_dirs.p, n, r->hist.p,
-                                                                 r->dropped.p, d_refl.p);
-            r->launches++;
-            WVB_CUDA(cudaEventRecord(r->ev1, r->stream));
-            WVB_CUDA(cudaGetLastError());
-            if (P.keep_steps) {
-                WVB_CUDA(cudaMemcpyAsync(reflections, d_refl.p, (size_t)P.keep_steps * n * 32,
-                                         cudaMemcpyDeviceToHost, r->stream));
-            }
+        WVB_CUDA(cudaSetDevice(r->dev));
+        if (n && keep) d_refl.alloc((size_t)keep * n, false);
+        wvb_rt_trace_enqueue(r, p, directions, n, d_refl.p, keep);
+        if (n && keep) {
+            WVB_CUDA(cudaMemcpyAsync(reflections, d_refl.p, (size_t)keep * n * 32, cudaMemcpyDeviceToHost,
+                                     r->stream));
         }
         unsigned long long dr = 0;
         WVB_CUDA(cudaMemcpyAsync(&dr, r->dropped.p, 8, cudaMemcpyDeviceToHost, r->stream));
