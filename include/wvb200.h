@@ -366,6 +366,57 @@ wvb_status wvb_mesh_counts(const wvb_mesh* mesh, uint64_t counts[3]);
 wvb_status wvb_mesh_read(const wvb_mesh* mesh, wvb_condensed_node* nodes, uint32_t* b1, uint32_t* b2,
                          uint32_t* b3, uint8_t* inside);
 
+/* ---- image-source stage (the consumer of the first reflections of every ray) ---- */
+
+typedef struct wvb_is wvb_is;
+
+/* raytracer::impulse<8> (src/raytracer/include/raytracer/cl/structs.h:37-44), 64 B */
+typedef struct {
+    float volume[8];
+    float position[4]; /* cl_float3 */
+    float distance;
+    float pad_[3];
+} wvb_impulse;
+
+typedef struct {
+    float source[3], receiver[3];
+    double acoustic_impedance; /* core::environment (400 by default) */
+    int32_t flip_phase;        /* postprocess_branches' flag; image_source_processor passes false */
+    int32_t with_direct;       /* append get_direct's impulse (image_source.cpp:53-58) */
+    uint64_t max_elements;     /* upper bound on rays x order over all pushes (sizes the node table) */
+} wvb_is_desc;
+
+/* What reflection_processor::make_image_source builds on the host
+ * (reflection_processor/image_source.h:15-86, image_source.cpp:12-68):
+ *   push      image_source_group_processor::process + image_source_processor::accumulate:
+ *             the (triangle, visible) elements of every ray's first `order` reflections are
+ *             merged into the multitree (tree.cpp:185-199, multitree.h:28-36)
+ *   results   image_source_processor::get_results: find_valid_paths over the tree
+ *             (tree.cpp:201-218) with fast_pressure_calculator, the direct impulse, the
+ *             distance correction; impulses in the reference's tree order (pre-order by
+ *             triangle index), the direct one last.
+ * The tree lives on the device as a hash table of (parent node, triangle) keys; every
+ * visible node is validated by one thread (csrc/is_kernels.cuh). */
+wvb_status wvb_is_create(wvb_rt* scene, const wvb_is_desc* desc, wvb_is** out);
+void wvb_is_destroy(wvb_is* is);
+/* elements: [order][n_rays] u32 = triangle | 0x80000000 if receiver_visible, or
+ * 0xffffffff where the ray had stopped (reflection_path_builder.h:16-26).
+ * ray_index_base: global index of ray 0 (decides whose `visible` flag a node keeps). */
+wvb_status wvb_is_push_elements(wvb_is* is, const uint32_t* elements, uint64_t n_rays, uint32_t order,
+                                uint64_t ray_index_base);
+/* the same from reflection records [steps][n_rays] as wvb_rt_trace returns them */
+wvb_status wvb_is_push_reflections(wvb_is* is, const wvb_reflection* reflections, uint64_t n_rays,
+                                   uint32_t steps, uint64_t ray_index_base);
+/* raytracer::run for n_rays (wvb_rt_trace) with the first `order` reflections handed
+ * to the tree on the device: no reflection leaves the GPU. */
+wvb_status wvb_is_trace(wvb_is* is, const wvb_rt_trace_params* params, const float* directions,
+                        uint64_t n_rays, uint32_t order, uint64_t* dropped, float* device_ms);
+/* out may be NULL (count only). stats (optional): [0] tree nodes, [1] visible nodes,
+ * [2] paths abandoned because a ray would start at its target (the reference throws),
+ * [3] malformed elements ignored. device_ms (optional): validation kernel time. */
+wvb_status wvb_is_results(wvb_is* is, wvb_impulse* out, uint64_t cap, uint64_t* count,
+                          uint64_t stats[4], float* device_ms);
+
 /* ---- test hooks ------------------------------------------------------------- */
 /* The reference's device filter test kernels (cl/filters.cpp:56-75): n_streams
  * parallel filters fed input[sample][stream] (float), output likewise.

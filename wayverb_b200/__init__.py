@@ -9,8 +9,8 @@ from . import _lib  # noqa: F401
 from .waveguide import (Mesh, Waveguide, build_mesh, cuboid_mesh, hard_source, soft_source, node_receiver,  # noqa: F401
                         run, slab_range)
 
-from .raytracer import RayTracer, reflection_depth  # noqa: F401,E402
+from .raytracer import ImageSource, RayTracer, reflection_depth  # noqa: F401,E402
 from . import scene  # noqa: F401,E402
 
-__all__ = ["build_mesh", "RayTracer", "reflection_depth", "scene", "Mesh", "Waveguide", "cuboid_mesh", "hard_source", "soft_source", "node_receiver", "run",
+__all__ = ["build_mesh", "ImageSource", "RayTracer", "reflection_depth", "scene", "Mesh", "Waveguide", "cuboid_mesh", "hard_source", "soft_source", "node_receiver", "run",
            "slab_range"]

@@ -85,6 +85,18 @@ class RtTraceParams(C.Structure):
     ]
 
 
+class IsDesc(C.Structure):
+    _fields_ = [
+        ("source", C.c_float * 3), ("receiver", C.c_float * 3),
+        ("acoustic_impedance", C.c_double), ("flip_phase", C.c_int32), ("with_direct", C.c_int32),
+        ("max_elements", C.c_uint64),
+    ]
+
+
+IMPULSE_DT = np.dtype([("volume", "<f4", (8,)), ("position", "<f4", (4,)), ("distance", "<f4"),
+                       ("pad_", "<f4", (3,))])  # raytracer::impulse<8>
+assert IMPULSE_DT.itemsize == 64
+
 # every symbol include/wvb200.h declares (tests check the .so exports them all)
 WG_SYMBOLS = [
     "wvb_wg_create", "wvb_wg_destroy", "wvb_wg_write_f64", "wvb_wg_read_f64", "wvb_wg_read_field",
@@ -96,6 +108,9 @@ WG_SYMBOLS = [
 ]
 
 MESH_SYMBOLS = ["wvb_mesh_create", "wvb_mesh_destroy", "wvb_mesh_counts", "wvb_mesh_read"]
+
+IS_SYMBOLS = ["wvb_is_create", "wvb_is_destroy", "wvb_is_push_elements", "wvb_is_push_reflections",
+              "wvb_is_trace", "wvb_is_results"]
 
 RT_SYMBOLS = [
     "wvb_rt_create", "wvb_rt_destroy", "wvb_rt_trace", "wvb_rt_read_histogram", "wvb_rt_reset_histogram",
@@ -166,6 +181,13 @@ def lib():
     L.wvb_rt_safe_bins.argtypes = [vp, u32, C.c_double, C.c_double]
     L.wvb_rt_closest_hit.argtypes = [vp, vp, u64, vp, vp]
     L.wvb_rt_directions.argtypes = [vp, u64, u64, u64, vp]
+    L.wvb_is_create.argtypes = [vp, C.POINTER(IsDesc), C.POINTER(vp)]
+    L.wvb_is_destroy.argtypes = [vp]
+    L.wvb_is_destroy.restype = None
+    L.wvb_is_push_elements.argtypes = [vp, vp, u64, u32, u64]
+    L.wvb_is_push_reflections.argtypes = [vp, vp, u64, u32, u64]
+    L.wvb_is_trace.argtypes = [vp, C.POINTER(RtTraceParams), vp, u64, u32, C.POINTER(u64), C.POINTER(C.c_float)]
+    L.wvb_is_results.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64 * 4), C.POINTER(C.c_float)]
     _lib = L
     return L
 

@@ -14,7 +14,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import RtSceneDesc, RtTraceParams, check, lib, ptr
+from ._lib import IMPULSE_DT, IsDesc, RtSceneDesc, RtTraceParams, check, lib, ptr
 from .scene import REFL_DT, Scene
 
 
@@ -75,6 +75,17 @@ class RayTracer:
         """dirs: n x 3 float32 or None (generate n_rays directions on the device).
         Returns (reflections or None, dropped, device_ms); the histogram accumulates on the
         device, read it with histogram()."""
+        d, n, P = self._params(dirs, source, receiver, depth, n_rays, total_rays, receiver_radius, speed_of_sound,
+                               histogram_rate, seed, ray_index_base, specular_from_step, n_bins, directional,
+                               keep_steps)
+        refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
+        dropped, ms = C.c_uint64(0), C.c_float(0)
+        check(lib().wvb_rt_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n,
+                                 ptr(refl) if refl is not None else None, C.byref(dropped), C.byref(ms)))
+        return refl, dropped.value, ms.value
+
+    def _params(self, dirs, source, receiver, depth, n_rays, total_rays, receiver_radius, speed_of_sound,
+                histogram_rate, seed, ray_index_base, specular_from_step, n_bins, directional, keep_steps):
         if dirs is not None:
             d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
             n = d.shape[0]
@@ -91,11 +102,7 @@ class RayTracer:
         P.n_bins = self.safe_bins(depth, speed_of_sound, histogram_rate) if n_bins is None else int(n_bins)
         P.directional, P.keep_steps = int(bool(directional)), int(keep_steps)
         self._shape = (20, 9, P.n_bins, 8) if directional else (P.n_bins, 8)
-        refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
-        dropped, ms = C.c_uint64(0), C.c_float(0)
-        check(lib().wvb_rt_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n,
-                                 ptr(refl) if refl is not None else None, C.byref(dropped), C.byref(ms)))
-        return refl, dropped.value, ms.value
+        return d, n, P
 
     def histogram(self) -> np.ndarray:
         out = np.zeros(self._shape)
@@ -116,3 +123,69 @@ class RayTracer:
         out = np.zeros((n, 3), np.float32)
         check(lib().wvb_rt_directions(self._h, int(seed), int(base), int(n), ptr(out)))
         return out
+
+
+class ImageSource:
+    """reflection_processor::make_image_source on the device
+    (reflection_processor/image_source.h:15-86): push the first reflections of every
+    ray (from the host, or straight from a trace), then results() = get_results()."""
+
+    def __init__(self, tracer: RayTracer, source, receiver, max_elements, acoustic_impedance=400.0,
+                 flip_phase=False, with_direct=True):
+        self.tracer = tracer
+        self.source, self.receiver = tuple(map(float, source)), tuple(map(float, receiver))
+        d = IsDesc()
+        d.source[:] = self.source
+        d.receiver[:] = self.receiver
+        d.acoustic_impedance = float(acoustic_impedance)
+        d.flip_phase, d.with_direct = int(bool(flip_phase)), int(bool(with_direct))
+        d.max_elements = int(max_elements)
+        h = C.c_void_p()
+        check(lib().wvb_is_create(tracer._h, C.byref(d), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().wvb_is_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def push_elements(self, elems, ray_index_base=0):
+        e = np.ascontiguousarray(elems, np.uint32)
+        order, n = e.shape
+        check(lib().wvb_is_push_elements(self._h, ptr(e), n, order, int(ray_index_base)))
+
+    def push_reflections(self, refl, ray_index_base=0):
+        r = np.ascontiguousarray(refl, REFL_DT)
+        steps, n = r.shape
+        check(lib().wvb_is_push_reflections(self._h, ptr(r), n, steps, int(ray_index_base)))
+
+    def trace(self, dirs, depth, order, n_rays=None, total_rays=None, receiver_radius=0.1, speed_of_sound=340.0,
+              histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0, n_bins=None,
+              directional=False):
+        d, n, P = self.tracer._params(dirs, self.source, self.receiver, depth, n_rays, total_rays, receiver_radius,
+                                      speed_of_sound, histogram_rate, seed, ray_index_base, specular_from_step,
+                                      n_bins, directional, 0)
+        dropped, ms = C.c_uint64(0), C.c_float(0)
+        check(lib().wvb_is_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n, int(order),
+                                 C.byref(dropped), C.byref(ms)))
+
+    def results(self):
+        """-> (impulses, stats[4], validation kernel ms)"""
+        count, ms = C.c_uint64(0), C.c_float(0)
+        stats = (C.c_uint64 * 4)()
+        check(lib().wvb_is_results(self._h, None, 0, C.byref(count), C.byref(stats), C.byref(ms)))
+        out = np.zeros(count.value, IMPULSE_DT)
+        check(lib().wvb_is_results(self._h, ptr(out), out.size, C.byref(count), C.byref(stats), C.byref(ms)))
+        return out[:count.value], np.array(list(stats), np.uint64), ms.value
