@@ -86,6 +86,15 @@ struct alignas(16) reflection final {
 };
 static_assert(sizeof(reflection) == sizeof(wvb_reflection), "reflection layout");
 
+/// raytracer/cl/structs.h:37-44
+template <size_t channels>
+struct alignas(1 << 5) impulse final {
+    core::bands_type volume;  // channels == simulation_bands == 8 is the only instantiation in use
+    cl_float3 position;
+    cl_float distance;
+};
+static_assert(sizeof(impulse<8>) == sizeof(wvb_impulse), "impulse<8> layout");
+
 /// compute_optimum_reflection_number (optimum_reflection_number.h:38-68)
 inline size_t compute_optimum_reflection_number(double absorption) {
     return wvb_rt_reflection_depth(absorption);
@@ -459,6 +468,40 @@ private:
     size_t max_order_;
 };
 
+/// reflection_processor::make_image_source (reflection_processor/image_source.h:15-86)
+/// evaluated on the device: the first `max_order` reflections of every ray feed the
+/// path tree straight from the trace kernel, validation and pressure calculation run
+/// as kernels (wvb_is_*), get_results() returns the reference's impulses in the
+/// reference's order. Same constructor as the reference.
+class device_image_source_processor final {
+public:
+    static constexpr bool device_resident = true;
+    explicit device_image_source_processor(size_t max_order) : max_order{max_order} {}
+    struct group final {
+        template <typename It>
+        void process(It, It, const core::scene_buffers&, size_t, size_t) {}
+    };
+    group get_group_processor(size_t) const { return {}; }
+    void accumulate(const group&) {}
+    util::aligned::vector<impulse<8>> get_results() const { return results; }
+
+    size_t max_order;
+    util::aligned::vector<impulse<8>> results;
+};
+class make_image_source final {
+public:
+    explicit make_image_source(size_t max_order) : max_order_{max_order} {}
+    template <typename Scene>
+    device_image_source_processor get_processor(const core::compute_context&, const core::vec3&,
+                                                const core::vec3&, const core::environment&,
+                                                const Scene&) const {
+        return device_image_source_processor{max_order_};
+    }
+
+private:
+    size_t max_order_;
+};
+
 }  // namespace reflection_processor
 
 namespace detail {
@@ -519,6 +562,34 @@ inline void store_histogram(reflection_processor::device_histogram_processor<tru
 template <typename T>
 void store_histogram(T&, const std::vector<double>&, size_t) {}
 
+// image-source request found among the processors (at most one is honoured)
+struct image_source_request final {
+    bool present{false};
+    size_t max_order{0};
+};
+inline void note_image_source(const reflection_processor::device_image_source_processor& p,
+                              image_source_request& r) {
+    if (!r.present) r = {true, p.max_order};
+}
+template <typename T>
+void note_image_source(const T&, image_source_request&) {}
+inline void store_image_source(reflection_processor::device_image_source_processor& p,
+                               const util::aligned::vector<impulse<8>>& v) {
+    p.results = v;
+}
+template <typename T>
+void store_image_source(T&, const util::aligned::vector<impulse<8>>&) {}
+
+struct is_handle final {
+    wvb_is* h{nullptr};
+    is_handle() = default;
+    is_handle(const is_handle&) = delete;
+    is_handle& operator=(const is_handle&) = delete;
+    ~is_handle() {
+        if (h) wvb_is_destroy(h);
+    }
+};
+
 }  // namespace detail
 
 namespace detail {
@@ -552,9 +623,11 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
     const size_t depth = compute_optimum_reflection_number(voxelised);     // :220-221
 
     detail::histogram_request hist;
+    detail::image_source_request img;
     size_t keep = 0;
     detail::for_each_in(processors, [&](auto& p, auto) {
         detail::note_histogram(p, hist);
+        detail::note_image_source(p, img);
         if (!detail::is_device_resident<std::decay_t<decltype(p)>>::value) {
             keep = std::max(keep, detail::steps_required_of(p, depth, 0));
         }
@@ -575,6 +648,19 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
     p.keep_steps = uint32_t(keep);
     core::detail::check(wvb_rt_reset_histogram(h.get()));
 
+    detail::is_handle is;
+    const size_t is_order = std::min(img.max_order, depth);
+    if (img.present) {
+        wvb_is_desc d{};
+        d.source[0] = source.x; d.source[1] = source.y; d.source[2] = source.z;
+        d.receiver[0] = receiver.x; d.receiver[1] = receiver.y; d.receiver[2] = receiver.z;
+        d.acoustic_impedance = environment.acoustic_impedance;
+        d.flip_phase = 0;   // image_source.cpp:49
+        d.with_direct = 1;  // image_source.cpp:53-58
+        d.max_elements = std::max<uint64_t>(1, uint64_t(total) * is_order);
+        core::detail::check(wvb_is_create(h.get(), &d, &is.h));
+    }
+
     std::vector<float> dirs;
     std::vector<reflection> refl;
     const auto run_segment = [&](It b, size_t n, size_t base) {
@@ -586,9 +672,13 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
         }
         refl.resize(keep * n);
         p.ray_index_base = base;
-        core::detail::check(wvb_rt_trace(h.get(), &p, dirs.data(), n,
-                                         keep ? reinterpret_cast<wvb_reflection*>(refl.data()) : nullptr,
-                                         nullptr, nullptr));
+        wvb_reflection* const host_refl = keep ? reinterpret_cast<wvb_reflection*>(refl.data()) : nullptr;
+        if (is.h) {
+            core::detail::check(wvb_is_trace(is.h, &p, dirs.data(), n, uint32_t(is_order), host_refl, nullptr,
+                                             nullptr));
+        } else {
+            core::detail::check(wvb_rt_trace(h.get(), &p, dirs.data(), n, host_refl, nullptr, nullptr));
+        }
         detail::for_each_in(processors, [&](auto& proc, auto) {
             auto group = proc.get_group_processor(n);
             if (!detail::is_device_resident<std::decay_t<decltype(proc)>>::value) {
@@ -616,6 +706,15 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
         std::vector<double> hbuf(size_t(p.n_bins) * 8 * (hist.directional ? 180 : 1));
         core::detail::check(wvb_rt_read_histogram(h.get(), hbuf.data()));
         detail::for_each_in(processors, [&](auto& proc, auto) { detail::store_histogram(proc, hbuf, p.n_bins); });
+    }
+    if (is.h) {
+        uint64_t count = 0;
+        core::detail::check(wvb_is_results(is.h, nullptr, 0, &count, nullptr, nullptr));
+        util::aligned::vector<impulse<8>> imps(count);
+        static_assert(sizeof(impulse<8>) == sizeof(wvb_impulse), "impulse<8> layout");
+        core::detail::check(wvb_is_results(is.h, reinterpret_cast<wvb_impulse*>(imps.data()), count, &count,
+                                           nullptr, nullptr));
+        detail::for_each_in(processors, [&](auto& proc, auto) { detail::store_image_source(proc, imps); });
     }
     return std::experimental::make_optional(detail::collect_results(processors, seq));
 }

@@ -408,9 +408,11 @@ wvb_status wvb_is_push_elements(wvb_is* is, const uint32_t* elements, uint64_t n
 wvb_status wvb_is_push_reflections(wvb_is* is, const wvb_reflection* reflections, uint64_t n_rays,
                                    uint32_t steps, uint64_t ray_index_base);
 /* raytracer::run for n_rays (wvb_rt_trace) with the first `order` reflections handed
- * to the tree on the device: no reflection leaves the GPU. */
+ * to the tree on the device: no reflection has to leave the GPU. reflections
+ * (optional): [params->keep_steps][n_rays] records for other, host-side consumers. */
 wvb_status wvb_is_trace(wvb_is* is, const wvb_rt_trace_params* params, const float* directions,
-                        uint64_t n_rays, uint32_t order, uint64_t* dropped, float* device_ms);
+                        uint64_t n_rays, uint32_t order, wvb_reflection* reflections, uint64_t* dropped,
+                        float* device_ms);
 /* out may be NULL (count only). stats (optional): [0] tree nodes, [1] visible nodes,
  * [2] paths abandoned because a ray would start at its target (the reference throws),
  * [3] malformed elements ignored. device_ms (optional): validation kernel time. */

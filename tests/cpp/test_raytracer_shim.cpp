@@ -8,6 +8,7 @@
 #include <cstring>
 #include <tuple>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "wayverb_b200/raytracer.hpp"
@@ -40,7 +41,7 @@ static core::flattened_scene shoebox(float sx, float sy, float sz, unsigned side
     return s;
 }
 
-int main() {
+int main(int argc, char** argv) {
     const auto scene = shoebox(5.56f, 3.97f, 2.81f, 4);
     const core::compute_context cc{};
     const core::vec3 source{1, 1, 1}, receiver{2, 3, 1.5f};
@@ -119,6 +120,42 @@ int main() {
         for (size_t i = 0; i < rays; i += 997) {
             if (std::memcmp(&paths[i][0], &res.first_reflections[0][i], sizeof(raytracer::reflection))) return 16;
         }
+    }
+    // canonical.cpp:9-20 as the reference spells it: make_image_source evaluated on the device
+    {
+        auto tup = raytracer::run(
+                dirs.begin(), dirs.end(), cc, scene, source, receiver, core::environment{}, true,
+                [&](auto, auto) {},
+                std::make_tuple(raytracer::reflection_processor::make_image_source{4},
+                                raytracer::reflection_processor::make_directional_histogram{rays, 4 + 1, 0.1f, 1000.0f},
+                                raytracer::reflection_processor::make_visual{32}),
+                1234);
+        if (!tup) return 17;
+        const auto& imps = std::get<0>(*tup);
+        if (imps.size() < 7) return 18;  // six first-order images + direct at the very least
+        const auto& direct = imps.back();  // image_source.cpp:53-58
+        if (direct.position.s[0] != source.x || direct.position.s[1] != source.y || direct.position.s[2] != source.z) return 19;
+        bool saw_x0_image = false;
+        for (const auto& i : imps) {
+            const float dx = i.position.s[0] - receiver.x, dy = i.position.s[1] - receiver.y, dz = i.position.s[2] - receiver.z;
+            if (std::fabs(std::sqrt(dx * dx + dy * dy + dz * dz) - i.distance) > 1e-4f) return 20;
+            saw_x0_image |= std::fabs(i.position.s[0] + source.x) < 1e-5f && std::fabs(i.position.s[1] - source.y) < 1e-5f &&
+                            std::fabs(i.position.s[2] - source.z) < 1e-5f;
+        }
+        if (!saw_x0_image) return 21;
+        if (std::get<2>(*tup).size() != 132) return 22;
+        if (argc > 1) {  // hand directions and impulses to the Python test, which re-derives them with the oracle
+            const std::string dir = argv[1];
+            FILE* f = std::fopen((dir + "/dirs.f32").c_str(), "wb");
+            if (!f) return 23;
+            std::fwrite(dirs.data(), sizeof(core::vec3), dirs.size(), f);
+            std::fclose(f);
+            f = std::fopen((dir + "/impulses.bin").c_str(), "wb");
+            if (!f) return 23;
+            std::fwrite(imps.data(), sizeof(imps[0]), imps.size(), f);
+            std::fclose(f);
+        }
+        std::printf("IMAGE_SOURCES %zu\n", imps.size());
     }
     std::printf("RT_SHIM_OK energy=%g bins=%zu\n", total, res.histogram.histogram.size());
     return 0;

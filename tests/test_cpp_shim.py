@@ -90,6 +90,42 @@ def test_gaussian_preprocessor_and_directional_receiver(tmp_path):
 @pytest.mark.gpu
 def test_raytracer_run_template(tmp_path):
     exe = build(tmp_path, "test_raytracer_shim")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "RT_SHIM_OK" in r.stdout
+    # make_image_source through raytracer::run == the oracle's image-source stage fed by the
+    # oracle's own trace of the same directions (same seed, same segments)
+    from oracle import rto
+    from wayverb_b200 import scene as S
+    dirs = np.fromfile(os.path.join(tmp_path, "dirs.f32"), np.float32).reshape(-1, 3)
+    got = np.fromfile(os.path.join(tmp_path, "impulses.bin"), rto.IMPULSE_DT)
+    sx, sy, sz = 5.56, 3.97, 2.81
+    X, Y, Z = (0, sx), (0, sy), (0, sz)
+    verts = [(X[i & 1], Y[(i >> 1) & 1], Z[(i >> 2) & 1]) for i in range(8)]
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tris = []
+    for q in quads:
+        tris += [(0, q[0], q[1], q[2]), (0, q[0], q[2], q[3])]
+    sc = S.Scene(np.array(verts, np.float32), np.array(tris, np.uint32).view(S.TRI_DT).reshape(-1),
+                 [S.make_surface(0.1, 0.1)], side=4)
+    # the C++ test lists every triangle in every voxel and pads the box by 0.1
+    sc.aabb = np.array([-0.1, -0.1, -0.1, sx + 0.1, sy + 0.1, sz + 0.1], np.float32)
+    cells = 4 ** 3
+    flat = list(range(cells))
+    for c in range(cells):
+        flat[c] = len(flat)
+        flat += [len(tris)] + list(range(len(tris)))
+    sc.voxel_index = np.array(flat, np.uint32)
+    o = rto.Scene(sc)
+    src, rcv = (1, 1, 1), (2, 3, 1.5)
+    n = dirs.shape[0]
+    elems = np.zeros((4, n), np.uint32)
+    seg = 1 << 14
+    for b in range(0, n, seg):  # raytracer.h:219-244: segments of 16384 rays, global ray index base
+        e = min(n, b + seg)
+        # only the first four steps matter here; a ray's path does not depend on the depth limit
+        _, refl, _ = o.trace(dirs[b:e], src, rcv, depth=4, total_rays=n, seed=1234, ray_index_base=b,
+                             keep_steps=4, specular_from_step=5, n_bins=8)
+        elems[:, b:e] = rto.path_elements(refl, 4)
+    want, _ = rto.image_source(o, elems, src, rcv)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint8), want.view(np.uint8))

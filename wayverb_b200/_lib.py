@@ -186,7 +186,8 @@ def lib():
     L.wvb_is_destroy.restype = None
     L.wvb_is_push_elements.argtypes = [vp, vp, u64, u32, u64]
     L.wvb_is_push_reflections.argtypes = [vp, vp, u64, u32, u64]
-    L.wvb_is_trace.argtypes = [vp, C.POINTER(RtTraceParams), vp, u64, u32, C.POINTER(u64), C.POINTER(C.c_float)]
+    L.wvb_is_trace.argtypes = [vp, C.POINTER(RtTraceParams), vp, u64, u32, vp, C.POINTER(u64),
+                               C.POINTER(C.c_float)]
     L.wvb_is_results.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64 * 4), C.POINTER(C.c_float)]
     _lib = L
     return L

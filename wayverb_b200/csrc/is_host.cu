@@ -37,6 +37,13 @@ struct wvb_is {
     uint32_t max_order = 0;
     dev_buf<unsigned long long> keys, first, counters;
     dev_buf<float> image, impedance;
+    dev_buf<is::Impulse> d_imp;  // grown on demand, kept between results() calls
+    dev_buf<uint32_t> d_list;    // slots of the visible nodes
+    // results of the last validation, valid until the next push
+    bool cached = false;
+    std::vector<is::Impulse> ordered;
+    uint64_t cached_stats[4] = {0, 0, 0, 0};
+    float cached_ms = 0;
     is::Table tab{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~wvb_is() {
@@ -69,6 +76,7 @@ void push_device(wvb_is* s, const uint32_t* d_elems, const rt::ReflectionPod* d_
                 (unsigned long long)(s->pushed + (uint64_t)n * order), (unsigned long long)s->max_elements);
     s->pushed += (uint64_t)n * order;
     s->max_order = std::max(s->max_order, order);
+    s->cached = false;
     const rt::Scene* sc = wvb_rt_device_scene(s->scene, nullptr);
     is::is_insert<<<(n + 127) / 128, 128, 0, s->stream>>>(s->tab, *sc, s->q.source, d_elems, d_refl, n, order,
                                                           ray_base, s->counters.p);
@@ -174,17 +182,23 @@ wvb_status wvb_is_push_reflections(wvb_is* s, const wvb_reflection* reflections,
 }
 
 wvb_status wvb_is_trace(wvb_is* s, const wvb_rt_trace_params* p, const float* directions, uint64_t n_rays,
-                        uint32_t order, uint64_t* dropped, float* device_ms) {
+                        uint32_t order, wvb_reflection* reflections, uint64_t* dropped, float* device_ms) {
     if (!s || !p) return WVB_ERR_INVALID;
     return guarded([&] {
         WVB_REQUIRE(n_rays < 0xffffffffull, WVB_ERR_UNSUPPORTED, "too many rays in one call");
         WVB_CUDA(cudaSetDevice(s->dev));
         const uint32_t n = (uint32_t)n_rays;
-        const uint32_t keep = std::min(order, p->depth);  // steps beyond depth do not exist
+        const uint32_t to_tree = std::min(order, p->depth);  // steps beyond depth do not exist
+        const uint32_t to_host = reflections ? p->keep_steps : 0u;
+        const uint32_t keep = std::max(to_tree, to_host);
         dev_buf<rt::ReflectionPod> d;
         if (n && keep) d.alloc((size_t)n * keep, false);
         wvb_rt_trace_enqueue(s->scene, p, directions, n, d.p, keep);
-        push_device(s, nullptr, d.p, n, keep, p->ray_index_base);
+        push_device(s, nullptr, d.p, n, to_tree, p->ray_index_base);
+        if (n && to_host) {
+            WVB_CUDA(cudaMemcpyAsync(reflections, d.p, (size_t)to_host * n * 32, cudaMemcpyDeviceToHost,
+                                     s->stream));
+        }
         WVB_CUDA(cudaStreamSynchronize(s->stream));
         if (dropped) *dropped = 0;  // the histogram's drop counter stays with the scene handle
         if (device_ms) *device_ms = 0;
@@ -196,84 +210,90 @@ wvb_status wvb_is_results(wvb_is* s, wvb_impulse* out, uint64_t cap, uint64_t* c
     if (!s || !count) return WVB_ERR_INVALID;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(s->dev));
-        const rt::Scene* sc = wvb_rt_device_scene(s->scene, nullptr);
-        unsigned long long c[8];
-        // the emit counters restart; nodes / bad elements accumulate over pushes
-        WVB_CUDA(cudaMemsetAsync(s->counters.p + 1, 0, 8, s->stream));
-        WVB_CUDA(cudaMemsetAsync(s->counters.p + 2, 0, 8, s->stream));
-        WVB_CUDA(cudaMemsetAsync(s->counters.p + 4, 0, 8, s->stream));
-        WVB_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
-        WVB_CUDA(cudaStreamSynchronize(s->stream));
-        // every visible node can yield at most one impulse; size for the node count
-        const uint64_t nodes = c[0];
-        dev_buf<is::Impulse> d_imp;
-        d_imp.alloc(std::max<uint64_t>(nodes, 1) + 1, false);
-        const size_t slots = (size_t)s->tab.mask + 1;
-        WVB_CUDA(cudaEventRecord(s->ev0, s->stream));
-        is::is_validate<<<(unsigned)((slots + 127) / 128), 128, 0, s->stream>>>(
-                s->tab, *sc, s->q, s->impedance.p, d_imp.p, nodes, s->counters.p);
-        WVB_CUDA(cudaEventRecord(s->ev1, s->stream));
-        WVB_CUDA(cudaGetLastError());
-        WVB_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
-        WVB_CUDA(cudaStreamSynchronize(s->stream));
-        const uint64_t n_valid = std::min<uint64_t>(c[4], nodes);
-        std::vector<is::Impulse> imps(n_valid + 1);
-        std::vector<uint32_t> chains;
-        const uint32_t width = std::max(s->max_order, 1u);
-        if (n_valid) {
-            dev_buf<uint32_t> d_chain;
-            d_chain.alloc((size_t)n_valid * width, false);
-            is::is_chains<<<(unsigned)((n_valid + 127) / 128), 128, 0, s->stream>>>(
-                    s->tab, d_imp.p, (uint32_t)n_valid, width, d_chain.p);
-            WVB_CUDA(cudaGetLastError());
-            chains.resize((size_t)n_valid * width);
-            WVB_CUDA(cudaMemcpyAsync(chains.data(), d_chain.p, chains.size() * 4, cudaMemcpyDeviceToHost,
-                                     s->stream));
-            WVB_CUDA(cudaMemcpyAsync(imps.data(), d_imp.p, n_valid * sizeof(is::Impulse),
-                                     cudaMemcpyDeviceToHost, s->stream));
+        if (!s->cached) {
+            const rt::Scene* sc = wvb_rt_device_scene(s->scene, nullptr);
+            unsigned long long c[8];
+            // the emit counters restart; nodes / bad elements accumulate over pushes
+            WVB_CUDA(cudaMemsetAsync(s->counters.p + 1, 0, 16, s->stream));
+            WVB_CUDA(cudaMemsetAsync(s->counters.p + 4, 0, 8, s->stream));
+            WVB_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
             WVB_CUDA(cudaStreamSynchronize(s->stream));
-        }
-        uint32_t have_direct = 0;
-        if (s->with_direct) {
+            // every visible node yields at most one impulse; slot `nodes` takes the direct one
+            const uint64_t nodes = c[0];
+            if (s->d_imp.n < nodes + 1) s->d_imp.alloc(nodes + 1 + nodes / 4, false);
+            if (s->d_list.n < nodes + 1) s->d_list.alloc(nodes + 1 + nodes / 4, false);
+            const size_t slots = (size_t)s->tab.mask + 1;
             dev_buf<uint32_t> d_have;
             d_have.alloc(1, true);
-            is::is_direct<<<1, 1, 0, s->stream>>>(*sc, s->q, d_imp.p + nodes, d_have.p);
+            WVB_CUDA(cudaEventRecord(s->ev0, s->stream));
+            is::is_collect<<<(unsigned)((slots + 255) / 256), 256, 0, s->stream>>>(s->tab, s->d_list.p,
+                                                                                   s->counters.p);
             WVB_CUDA(cudaGetLastError());
-            WVB_CUDA(cudaMemcpyAsync(&have_direct, d_have.p, 4, cudaMemcpyDeviceToHost, s->stream));
-            WVB_CUDA(cudaMemcpyAsync(&imps[n_valid], d_imp.p + nodes, sizeof(is::Impulse),
-                                     cudaMemcpyDeviceToHost, s->stream));
+            WVB_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
             WVB_CUDA(cudaStreamSynchronize(s->stream));
-        }
-        // the reference's order: depth-first over branches sorted by triangle index
-        // (tree.h:33-35, multitree.h:38-58), i.e. lexicographic with a prefix first
-        std::vector<uint32_t> order(n_valid);
-        std::iota(order.begin(), order.end(), 0u);
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return std::lexicographical_compare(chains.begin() + (size_t)a * width,
-                                                chains.begin() + (size_t)(a + 1) * width,
-                                                chains.begin() + (size_t)b * width,
-                                                chains.begin() + (size_t)(b + 1) * width);
-        });
-        const uint64_t total = n_valid + (have_direct ? 1 : 0);
-        *count = total;
-        if (out) {
-            uint64_t w = 0;
-            auto emit = [&](is::Impulse v) {
-                if (w >= cap) return;
+            const uint32_t n_list = (uint32_t)c[1];
+            if (n_list) {
+                is::is_validate<<<(n_list + 127) / 128, 128, 0, s->stream>>>(
+                        s->tab, *sc, s->q, s->impedance.p, s->d_list.p, n_list, s->d_imp.p, nodes,
+                        s->counters.p);
+            }
+            WVB_CUDA(cudaEventRecord(s->ev1, s->stream));
+            WVB_CUDA(cudaGetLastError());
+            uint32_t have_direct = 0;
+            if (s->with_direct) {
+                is::is_direct<<<1, 1, 0, s->stream>>>(*sc, s->q, s->d_imp.p + nodes, d_have.p);
+                WVB_CUDA(cudaGetLastError());
+                WVB_CUDA(cudaMemcpyAsync(&have_direct, d_have.p, 4, cudaMemcpyDeviceToHost, s->stream));
+            }
+            WVB_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+            WVB_CUDA(cudaStreamSynchronize(s->stream));
+            const uint64_t n_valid = std::min<uint64_t>(c[4], nodes);
+            std::vector<is::Impulse> imps(n_valid + 1);
+            std::vector<uint32_t> chains;
+            const uint32_t width = std::max(s->max_order, 1u);
+            if (n_valid) {
+                dev_buf<uint32_t> d_chain;
+                d_chain.alloc((size_t)n_valid * width, false);
+                is::is_chains<<<(unsigned)((n_valid + 127) / 128), 128, 0, s->stream>>>(
+                        s->tab, s->d_imp.p, (uint32_t)n_valid, width, d_chain.p);
+                WVB_CUDA(cudaGetLastError());
+                chains.resize((size_t)n_valid * width);
+                WVB_CUDA(cudaMemcpyAsync(chains.data(), d_chain.p, chains.size() * 4, cudaMemcpyDeviceToHost,
+                                         s->stream));
+                WVB_CUDA(cudaMemcpyAsync(imps.data(), s->d_imp.p, n_valid * sizeof(is::Impulse),
+                                         cudaMemcpyDeviceToHost, s->stream));
+            }
+            if (have_direct) {
+                WVB_CUDA(cudaMemcpyAsync(&imps[n_valid], s->d_imp.p + nodes, sizeof(is::Impulse),
+                                         cudaMemcpyDeviceToHost, s->stream));
+            }
+            WVB_CUDA(cudaStreamSynchronize(s->stream));
+            // the reference's order: depth-first over branches sorted by triangle index
+            // (tree.h:33-35, multitree.h:38-58), i.e. lexicographic with a prefix first
+            std::vector<uint32_t> order(n_valid);
+            std::iota(order.begin(), order.end(), 0u);
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                return std::lexicographical_compare(chains.begin() + (size_t)a * width,
+                                                    chains.begin() + (size_t)(a + 1) * width,
+                                                    chains.begin() + (size_t)b * width,
+                                                    chains.begin() + (size_t)(b + 1) * width);
+            });
+            s->ordered.clear();
+            s->ordered.reserve(n_valid + 1);
+            auto keep = [&](is::Impulse v) {
                 v.slot = v.depth = v.pad_ = 0;
-                std::memcpy(out + w, &v, sizeof v);
-                ++w;
+                s->ordered.push_back(v);
             };
-            for (uint32_t i : order) emit(imps[i]);
-            if (have_direct) emit(imps[n_valid]);
+            for (uint32_t i : order) keep(imps[i]);
+            if (have_direct) keep(imps[n_valid]);
+            for (int k = 0; k < 4; ++k) s->cached_stats[k] = c[k];
+            WVB_CUDA(cudaEventElapsedTime(&s->cached_ms, s->ev0, s->ev1));
+            s->cached = true;
         }
-        if (stats) {
-            stats[0] = c[0];
-            stats[1] = c[1];
-            stats[2] = c[2];
-            stats[3] = c[3];
-        }
-        if (device_ms) WVB_CUDA(cudaEventElapsedTime(device_ms, s->ev0, s->ev1));
+        *count = s->ordered.size();
+        if (out) std::memcpy(out, s->ordered.data(), std::min<uint64_t>(cap, s->ordered.size()) * sizeof(wvb_impulse));
+        if (stats) std::memcpy(stats, s->cached_stats, sizeof s->cached_stats);
+        if (device_ms) *device_ms = s->cached_ms;
     });
 }
 

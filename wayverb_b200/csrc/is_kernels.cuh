@@ -245,15 +245,31 @@ __device__ __forceinline__ bool cpu_intersects(const Scene& sc, const Ray& r, ui
 // ---- validation ------------------------------------------------------------------
 // counters: [0] nodes, [1] visible nodes, [2] construct_ray failures, [3] bad elements,
 //           [4] impulses emitted
+// The table is at most half full and only visible nodes are validated: gather their
+// slots into a dense list first (warp-aggregated append), so that the validation
+// kernel starts with full warps.
+static __global__ void is_collect(Table tab, uint32_t* __restrict__ list,
+                                  unsigned long long* __restrict__ counters) {
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    if (slot <= tab.mask) take = tab.keys[slot] != KEY_EMPTY && (tab.first[slot] & 1ull);
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counters + 1, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)slot;
+}
+
 static __global__ void __launch_bounds__(128)
 is_validate(Table tab, Scene sc, Query q, const float* __restrict__ impedance /* [surface][8] */,
-            Impulse* __restrict__ out, unsigned long long cap,
-            unsigned long long* __restrict__ counters) {
-    const size_t slot0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot0 > tab.mask) return;
-    const unsigned long long key0 = tab.keys[slot0];
-    if (key0 == KEY_EMPTY || !(tab.first[slot0] & 1ull)) return;
-    atomicAdd(counters + 1, 1ull);
+            const uint32_t* __restrict__ list, uint32_t n_list, Impulse* __restrict__ out,
+            unsigned long long cap, unsigned long long* __restrict__ counters) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_list) return;
+    const size_t slot0 = list[li];
     const f3 final_image = rt::mk(tab.image[3 * slot0], tab.image[3 * slot0 + 1], tab.image[3 * slot0 + 2]);
     if (eq3(q.receiver, final_image)) return;  // tree.cpp:108-111
 

@@ -173,13 +173,17 @@ class ImageSource:
 
     def trace(self, dirs, depth, order, n_rays=None, total_rays=None, receiver_radius=0.1, speed_of_sound=340.0,
               histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0, n_bins=None,
-              directional=False):
+              directional=False, keep_steps=0):
+        """traces and feeds the tree on the device; returns the reflections of the first
+        keep_steps steps (or None) for host-side consumers"""
         d, n, P = self.tracer._params(dirs, self.source, self.receiver, depth, n_rays, total_rays, receiver_radius,
                                       speed_of_sound, histogram_rate, seed, ray_index_base, specular_from_step,
-                                      n_bins, directional, 0)
+                                      n_bins, directional, keep_steps)
+        refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
         dropped, ms = C.c_uint64(0), C.c_float(0)
         check(lib().wvb_is_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n, int(order),
-                                 C.byref(dropped), C.byref(ms)))
+                                 ptr(refl) if refl is not None else None, C.byref(dropped), C.byref(ms)))
+        return refl
 
     def results(self):
         """-> (impulses, stats[4], validation kernel ms)"""
