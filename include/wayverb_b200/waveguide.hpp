@@ -18,9 +18,11 @@
 // convert, so callers that keep float (e.g. directional_receiver) are unchanged.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <cmath>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -168,6 +170,81 @@ struct boundary_index_data final {
 static_assert(sizeof(condensed_node) == sizeof(wvb_condensed_node), "condensed_node layout");
 static_assert(sizeof(coefficients_canonical) == sizeof(wvb_coefficients_canonical),
               "coefficients_canonical layout");
+
+// ---- boundary filter design: fitted_boundary.h, arbitrary_magnitude_filter.h, stable.h --
+/// frequency_domain_envelope.h:9-31 (points kept in ascending frequency order)
+class frequency_domain_envelope final {
+public:
+    struct point final {
+        double frequency;
+        double amplitude;
+    };
+    using const_iterator = std::vector<point>::const_iterator;
+    const_iterator cbegin() const { return points.cbegin(); }
+    const_iterator cend() const { return points.cend(); }
+    void insert(point p) {
+        points.insert(std::lower_bound(points.begin(), points.end(), p,
+                                       [](const point& a, const point& b) { return a.frequency < b.frequency; }),
+                      p);
+    }
+
+private:
+    std::vector<point> points;
+};
+template <size_t N>
+frequency_domain_envelope make_frequency_domain_envelope(const std::array<double, N>& frequency,
+                                                         const std::array<double, N>& amplitude) {
+    frequency_domain_envelope ret;
+    for (size_t i = 0; i != N; ++i) ret.insert({frequency[i], amplitude[i]});
+    return ret;
+}
+/// arbitrary_magnitude_filter.h:63-95 (order 6 is the only one wayverb instantiates);
+/// the Yule-Walker fit runs in libwvb200.so instead of IT++
+template <size_t N>
+coefficients<N> arbitrary_magnitude_filter(const frequency_domain_envelope& env) {
+    static_assert(N == coefficients_canonical::order, "order 6 only");
+    std::vector<double> f, a;
+    for (auto it = env.cbegin(); it != env.cend(); ++it) {
+        f.push_back(it->frequency);
+        a.push_back(it->amplitude);
+    }
+    coefficients<N> ret;
+    core::detail::check(wvb_lrs_arbitrary_magnitude_filter(f.data(), a.data(), uint32_t(f.size()),
+                                                          reinterpret_cast<wvb_coefficients_canonical*>(&ret)));
+    return ret;
+}
+/// stable.h:37-50
+template <typename T>
+bool is_stable(const T& a) {
+    const std::vector<double> v(std::begin(a), std::end(a));
+    return wvb_lrs_is_stable(v.data(), uint32_t(v.size())) != 0;
+}
+/// fitted_boundary.h:34-50
+inline coefficients_canonical to_impedance_coefficients(const coefficients_canonical& c) {
+    coefficients_canonical ret;
+    wvb_lrs_to_impedance(reinterpret_cast<const wvb_coefficients_canonical*>(&c),
+                         reinterpret_cast<wvb_coefficients_canonical*>(&ret));
+    return ret;
+}
+/// fitted_boundary.h:72-75
+inline coefficients_canonical to_flat_coefficients(double absorption) {
+    coefficients_canonical ret;
+    wvb_lrs_flat(absorption, reinterpret_cast<wvb_coefficients_canonical*>(&ret));
+    return ret;
+}
+/// fitted_boundary.h:79-104; throws std::runtime_error("Unable to generate stable boundary
+/// filter.") like the reference
+template <typename T>
+coefficients_canonical compute_reflectance_filter_coefficients(const T& absorption, double sample_rate) {
+    double a[8];
+    size_t i = 0;
+    for (auto it = std::begin(absorption); it != std::end(absorption) && i < 8; ++it, ++i) a[i] = *it;
+    for (; i < 8; ++i) a[i] = 0;
+    coefficients_canonical ret;
+    const auto s = wvb_lrs_reflectance_filter(a, sample_rate, reinterpret_cast<wvb_coefficients_canonical*>(&ret));
+    if (s != WVB_OK) throw std::runtime_error{wvb_last_error()};
+    return ret;
+}
 
 struct alignas(16) mesh_descriptor final {
     static constexpr auto no_neighbor = ~cl_uint{0};

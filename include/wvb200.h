@@ -419,6 +419,25 @@ wvb_status wvb_is_trace(wvb_is* is, const wvb_rt_trace_params* params, const flo
 wvb_status wvb_is_results(wvb_is* is, wvb_impulse* out, uint64_t cap, uint64_t* count,
                           uint64_t stats[4], float* device_ms);
 
+/* ---- boundary filter design (host code, the step before wvb_wg_create) ------------ */
+/* What mesh.cpp:126-138 does per surface: absorption -> reflectance filter ->
+ * impedance filter. The reference's fit is itpp::yulewalk (IT++, un-vendored); this
+ * library carries its own implementation of that algorithm (csrc/lrs_design.cpp). */
+/* arbitrary_magnitude_filter<6> (arbitrary_magnitude_filter.h:63-95): envelope points
+ * (frequency in [0, 1] = dc..nyquist, amplitude), any order */
+wvb_status wvb_lrs_arbitrary_magnitude_filter(const double* frequency, const double* amplitude, uint32_t n,
+                                              wvb_coefficients_canonical* out);
+/* compute_reflectance_filter_coefficients (fitted_boundary.h:79-104); WVB_ERR_INVALID with
+ * the reference's message if the fit is unstable */
+wvb_status wvb_lrs_reflectance_filter(const double absorption[8], double sample_rate,
+                                      wvb_coefficients_canonical* out);
+/* to_impedance_coefficients (fitted_boundary.h:20-50) */
+void wvb_lrs_to_impedance(const wvb_coefficients_canonical* reflectance, wvb_coefficients_canonical* out);
+/* to_flat_coefficients (fitted_boundary.h:72-75) */
+void wvb_lrs_flat(double absorption, wvb_coefficients_canonical* out);
+/* is_stable (stable.h:11-50) on a denominator of n coefficients; 1 = stable */
+int wvb_lrs_is_stable(const double* a, uint32_t n);
+
 /* ---- test hooks ------------------------------------------------------------- */
 /* The reference's device filter test kernels (cl/filters.cpp:56-75): n_streams
  * parallel filters fed input[sample][stream] (float), output likewise.

@@ -28,6 +28,19 @@ def test_shim_compiles_as_cpp14(tmp_path):
     build(tmp_path, "test_raytracer_shim")
 
 
+def test_boundary_filter_design_through_the_shim(tmp_path):
+    """host code: runs here, no GPU (fitted_boundary.h call sequence vs the golden file)"""
+    import json
+    exe = build(tmp_path, "test_lrs_shim")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "LRS_SHIM_OK" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    rows = [np.array([float(v) for v in line.split()]) for line in r.stdout.splitlines()[:3]]
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "lrs_coefficients.json")))["sets"]
+    for row, s in zip(rows, golden[:3]):  # plaster, wood, concrete
+        want = np.concatenate([s["reflectance"]["b"], s["reflectance"]["a"], s["impedance"]["b"], s["impedance"]["a"]])
+        assert np.abs(row - want).max() < 1e-10
+
+
 @pytest.mark.gpu
 def test_waveguide_run_template_matches_oracle(tmp_path):
     exe = build(tmp_path, "test_waveguide_shim")

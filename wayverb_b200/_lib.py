@@ -109,6 +109,9 @@ WG_SYMBOLS = [
 
 MESH_SYMBOLS = ["wvb_mesh_create", "wvb_mesh_destroy", "wvb_mesh_counts", "wvb_mesh_read"]
 
+LRS_SYMBOLS = ["wvb_lrs_arbitrary_magnitude_filter", "wvb_lrs_reflectance_filter", "wvb_lrs_to_impedance",
+               "wvb_lrs_flat", "wvb_lrs_is_stable"]
+
 IS_SYMBOLS = ["wvb_is_create", "wvb_is_destroy", "wvb_is_push_elements", "wvb_is_push_reflections",
               "wvb_is_trace", "wvb_is_results"]
 
@@ -181,6 +184,14 @@ def lib():
     L.wvb_rt_safe_bins.argtypes = [vp, u32, C.c_double, C.c_double]
     L.wvb_rt_closest_hit.argtypes = [vp, vp, u64, vp, vp]
     L.wvb_rt_directions.argtypes = [vp, u64, u64, u64, vp]
+    L.wvb_lrs_arbitrary_magnitude_filter.argtypes = [vp, vp, u32, vp]
+    L.wvb_lrs_reflectance_filter.argtypes = [vp, C.c_double, vp]
+    L.wvb_lrs_to_impedance.argtypes = [vp, vp]
+    L.wvb_lrs_to_impedance.restype = None
+    L.wvb_lrs_flat.argtypes = [C.c_double, vp]
+    L.wvb_lrs_flat.restype = None
+    L.wvb_lrs_is_stable.argtypes = [vp, u32]
+    L.wvb_lrs_is_stable.restype = C.c_int
     L.wvb_is_create.argtypes = [vp, C.POINTER(IsDesc), C.POINTER(vp)]
     L.wvb_is_destroy.argtypes = [vp]
     L.wvb_is_destroy.restype = None
