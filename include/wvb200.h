@@ -329,6 +329,15 @@ wvb_status wvb_rt_trace(wvb_rt* rt, const wvb_rt_trace_params* params, const flo
                         float* device_ms);
 wvb_status wvb_rt_read_histogram(wvb_rt* rt, double* out);
 wvb_status wvb_rt_reset_histogram(wvb_rt* rt);
+/* Multi-GPU: rays are independent, so rank r traces its share of the
+ * directions (ray_index_base = first global ray index, total_rays = all ranks' rays)
+ * against a replicated scene and the histograms are added -- what sum_histograms
+ * (stochastic/postprocessing.h:72-90) does for the per-group histograms of one device.
+ * comm_init: once per handle, with the 128 bytes of wvb_nccl_unique_id from rank 0.
+ * allreduce_histogram: one fp64 ncclAllReduce(sum) of the device histogram, in place;
+ * every rank then reads the whole-job histogram. No-op on a handle without communicator. */
+wvb_status wvb_rt_comm_init(wvb_rt* rt, const void* nccl_unique_id, int32_t rank, int32_t nranks);
+wvb_status wvb_rt_allreduce_histogram(wvb_rt* rt);
 
 /* host helpers of the ray path */
 /* compute_optimum_reflection_number (optimum_reflection_number.h:38-40) */

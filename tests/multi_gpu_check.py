@@ -29,6 +29,39 @@ def plaster():
     return c
 
 
+def ray_check(rank, world, local):
+    """the ray path over NCCL: every rank traces its share, wvb_rt_allreduce_histogram sums;
+    rank 0 compares with the single-domain oracle (and with one GPU tracing everything)"""
+    from wayverb_b200 import scene
+    from wayverb_b200.slab import ray_range
+    from oracle import rto
+    total, depth, seed = 200000, 20, 33
+    src, rcv = (1.1, 1.2, 1.3), (3.0, 2.0, 4.5)
+    sc = scene.box_scene((4.0, 3.0, 6.0), subdiv=3, side=8, surfaces=[scene.make_surface(0.1, 0.2)])
+    box = [wvb.waveguide.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    b, e = ray_range(total, rank, world)
+    with wvb.RayTracer(sc, device=local) as g:
+        g.comm_init(box[0], rank, world)
+        g.trace(None, src, rcv, depth, n_rays=e - b, total_rays=total, seed=seed, ray_index_base=b, n_bins=500)
+        g.allreduce_histogram()
+        got = g.histogram()
+    ok = True
+    if rank == 0:
+        o = rto.Scene(sc)
+        want, _, _ = o.trace(rto.directions(seed, total), src, rcv, depth, seed=seed, n_bins=500)
+        with wvb.RayTracer(sc, device=local) as g1:
+            g1.trace(None, src, rcv, depth, n_rays=total, seed=seed, n_bins=500)
+            one = g1.histogram()
+        scale = np.abs(want).max()
+        err_o = np.abs(got - want).max() / scale
+        err_1 = np.abs(got - one).max() / scale
+        ok = err_o <= 1e-9 and err_1 <= 1e-9 and scale > 0
+        print("rays %d over %d ranks: all-reduced histogram vs oracle %.1e, vs one GPU %.1e (rel. to max bin)"
+              % (total, world, err_o, err_1), flush=True)
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -73,6 +106,7 @@ def main():
             print("dims %s kernel %s ranks %d: field identical=%s (rel RMS %.1e), traces identical=%s"
                   % (dims, info["kernel_variant"], world, same_f, rms, same_o), flush=True)
             ok = ok and same_f and same_o and wflag == 0
+    ok = ray_check(rank, world, local) and ok
     res = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(res, 0)
     dist.barrier()

@@ -118,7 +118,7 @@ IS_SYMBOLS = ["wvb_is_create", "wvb_is_destroy", "wvb_is_push_elements", "wvb_is
 RT_SYMBOLS = [
     "wvb_rt_create", "wvb_rt_destroy", "wvb_rt_trace", "wvb_rt_read_histogram", "wvb_rt_reset_histogram",
     "wvb_rt_reflection_depth", "wvb_rt_ray_energy", "wvb_rt_safe_bins", "wvb_rt_closest_hit",
-    "wvb_rt_directions",
+    "wvb_rt_directions", "wvb_rt_comm_init", "wvb_rt_allreduce_histogram",
 ]
 
 _lib = None
@@ -184,6 +184,8 @@ def lib():
     L.wvb_rt_safe_bins.argtypes = [vp, u32, C.c_double, C.c_double]
     L.wvb_rt_closest_hit.argtypes = [vp, vp, u64, vp, vp]
     L.wvb_rt_directions.argtypes = [vp, u64, u64, u64, vp]
+    L.wvb_rt_comm_init.argtypes = [vp, vp, i32, i32]
+    L.wvb_rt_allreduce_histogram.argtypes = [vp]
     L.wvb_lrs_arbitrary_magnitude_filter.argtypes = [vp, vp, u32, vp]
     L.wvb_lrs_reflectance_filter.argtypes = [vp, C.c_double, vp]
     L.wvb_lrs_to_impedance.argtypes = [vp, vp]

@@ -17,7 +17,7 @@ struct unique_id {
     char internal[128];
 };
 enum result_t { success = 0 };
-enum data_t { t_int8 = 0, t_uint8 = 1, t_int32 = 2, t_float32 = 7, t_float64 = 8 };
+enum data_t { t_int8 = 0, t_uint8 = 1, t_int32 = 2, t_uint64 = 5, t_float32 = 7, t_float64 = 8 };
 enum red_t { op_sum = 0, op_prod = 1, op_max = 2, op_min = 3 };
 
 struct api {

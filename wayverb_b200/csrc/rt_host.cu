@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.h"
+#include "nccl_dyn.h"
 #include "rt_kernels.cuh"
 
 using namespace wvb;
@@ -36,8 +37,11 @@ struct wvb_rt {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
+    nccl::comm_t comm = nullptr;  // multi-GPU: rays are split over ranks, histograms summed
+    int rank = 0, nranks = 1;
     ~wvb_rt() {
         cudaSetDevice(dev);
+        if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -264,6 +268,51 @@ wvb_status wvb_rt_trace(wvb_rt* r, const wvb_rt_trace_params* p, const float* di
             *device_ms = 0;
             if (n) WVB_CUDA(cudaEventElapsedTime(device_ms, r->ev0, r->ev1));
         }
+    });
+}
+
+wvb_status wvb_rt_comm_init(wvb_rt* r, const void* nccl_unique_id, int32_t rank, int32_t nranks) {
+    if (!r || !nccl_unique_id) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, WVB_ERR_INVALID, "rank %d of %d", rank, nranks);
+        WVB_REQUIRE(!r->comm, WVB_ERR_INVALID, "communicator already attached");
+        WVB_REQUIRE(nccl::get().ok, WVB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+        WVB_CUDA(cudaSetDevice(r->dev));
+        nccl::unique_id id;
+        std::memcpy(&id, nccl_unique_id, sizeof id);
+        const int rc = nccl::get().CommInitRank(&r->comm, nranks, id, rank);
+        if (rc != nccl::success) {
+            set_last_error("ncclCommInitRank failed: %s", nccl::get().GetErrorString(rc));
+            throw status_error{WVB_ERR_NCCL};
+        }
+        r->rank = rank;
+        r->nranks = nranks;
+    });
+}
+
+// sum_histograms over ranks (stochastic/postprocessing.h:72-90 adds the per-group
+// histograms; here the groups live on different GPUs): one fp64 ncclAllReduce of the
+// device-resident histogram and of the drop counter, in place
+wvb_status wvb_rt_allreduce_histogram(wvb_rt* r) {
+    if (!r) return WVB_ERR_INVALID;
+    return guarded([&] {
+        WVB_CUDA(cudaSetDevice(r->dev));
+        if (r->nranks <= 1 || !r->comm) return;
+        WVB_REQUIRE(r->hist.n > 0, WVB_ERR_INVALID, "no histogram yet (trace first)");
+        auto& n = nccl::get();
+        int rc = n.GroupStart();
+        if (rc == nccl::success) {
+            rc = n.AllReduce(r->hist.p, r->hist.p, r->hist.n, nccl::t_float64, nccl::op_sum, r->comm, r->stream);
+        }
+        if (rc == nccl::success) {
+            rc = n.AllReduce(r->dropped.p, r->dropped.p, 1, nccl::t_uint64, nccl::op_sum, r->comm, r->stream);
+        }
+        if (rc == nccl::success) rc = n.GroupEnd();
+        if (rc != nccl::success) {
+            set_last_error("ncclAllReduce failed: %s", n.GetErrorString(rc));
+            throw status_error{WVB_ERR_NCCL};
+        }
+        WVB_CUDA(cudaStreamSynchronize(r->stream));
     });
 }
 

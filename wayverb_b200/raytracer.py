@@ -104,6 +104,14 @@ class RayTracer:
         self._shape = (20, 9, P.n_bins, 8) if directional else (P.n_bins, 8)
         return d, n, P
 
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """attach an NCCL communicator (unique_id: wayverb_b200.waveguide.nccl_unique_id() of rank 0)"""
+        buf = np.frombuffer(unique_id, np.uint8).copy()
+        check(lib().wvb_rt_comm_init(self._h, ptr(buf), int(rank), int(nranks)))
+
+    def allreduce_histogram(self):
+        check(lib().wvb_rt_allreduce_histogram(self._h))
+
     def histogram(self) -> np.ndarray:
         out = np.zeros(self._shape)
         check(lib().wvb_rt_read_histogram(self._h, ptr(out)))

@@ -62,3 +62,11 @@ class SlabPlan:
 def make_plan(dz: int, rank: int, nranks: int) -> SlabPlan:
     z0, z1 = slab_range(dz, rank, nranks)
     return SlabPlan(rank, nranks, dz, z0, z1)
+
+
+def ray_range(total_rays: int, rank: int, nranks: int) -> Tuple[int, int]:
+    """The ray path's sharding: rays are independent, so rank r traces the
+    global rays [begin, end) -- `ray_index_base = begin`, `total_rays` = all ranks' rays --
+    against a replicated scene, and the histograms are summed over ranks
+    (wvb_rt_allreduce_histogram; sum_histograms, stochastic/postprocessing.h:72-90)."""
+    return total_rays * rank // nranks, total_rays * (rank + 1) // nranks
