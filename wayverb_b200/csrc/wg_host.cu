@@ -92,7 +92,11 @@ struct wvb_wg {
     int* h_flag = nullptr;  // pinned, 8 ints
     cudaStream_t stream = nullptr;
     cudaStream_t stream_b = nullptr;  // boundary kernel runs here, next to the air kernel
+    cudaStream_t stream_c = nullptr;  // ghost-plane exchange, underneath the interior update
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_faces = nullptr, ev_comm = nullptr;
+    int overlap_comm = 0;
+    int zchunks_inner = 1;
     int overlap = 1;
     int bminb = 4;
     int bpipe = 4;  // >0: pipelined 1-d boundary walk with this many blocks per SM
@@ -120,7 +124,10 @@ struct wvb_wg {
         if (step_graph) cudaGraphExecDestroy(step_graph);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_faces) cudaEventDestroy(ev_faces);
+        if (ev_comm) cudaEventDestroy(ev_comm);
         if (stream_b) cudaStreamDestroy(stream_b);
+        if (stream_c) cudaStreamDestroy(stream_c);
         if (stream) cudaStreamDestroy(stream);
         if (h_flag) cudaFreeHost(h_flag);
     }
@@ -263,14 +270,20 @@ void make_tensor_map(wvb_wg* w, int which, int ty) {
     WVB_REQUIRE(r == CUDA_SUCCESS, WVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 }
 
+// the owned planes [zbase, zbase + nplanes) in `zchunks` pieces
+struct ZWindow {
+    int zbase, nplanes, zchunks;
+};
+
 template <class Cfg>
-void launch_tma(wvb_wg* w, const double* cur, double* prev) {
+void launch_tma(wvb_wg* w, const double* cur, double* prev, ZWindow zw) {
     const WgGeom& g = w->g;
     (void)cur;  // read through the tensor map of P[w->cur]
     const int tiles_x = (g.dx + Cfg::TX - 1) / Cfg::TX, tiles_y = (g.dy + Cfg::TY - 1) / Cfg::TY;
-    const unsigned items = (unsigned)tiles_x * tiles_y * w->zchunks;
+    const unsigned items = (unsigned)tiles_x * tiles_y * zw.zchunks;
     wg_air_tma<Cfg><<<items, Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
-            w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, w->zchunks, w->flag.p);
+            w->map[w->cur], prev, w->code.p, g, tiles_x, tiles_y, zw.zchunks, zw.zbase, zw.nplanes,
+            w->flag.p);
 }
 
 // the TMA configurations that are compiled in: (TY, stages, fast division, min CTAs/SM)
@@ -294,27 +307,31 @@ bool with_tma_cfg(const wvb_wg* w, F&& f) {
 }
 
 template <bool FD, int PF>
-void launch_direct_t(wvb_wg* w, const double* cur, double* prev) {
+void launch_direct_t(wvb_wg* w, const double* cur, double* prev, ZWindow zw) {
     const WgGeom& g = w->g;
     constexpr int BX = 32, BY = 8;
-    const int zchunk = (g.nzl + w->zchunks - 1) / w->zchunks;
-    dim3 grid(((g.dx + 1) / 2 + BX - 1) / BX, (g.dy + BY - 1) / BY, (g.nzl + zchunk - 1) / zchunk);
-    wg_air_direct<BX, BY, FD, PF><<<grid, dim3(BX, BY), 0, w->stream>>>(cur, prev, w->code.p, g,
-                                                                         zchunk, w->flag.p);
+    const int zchunk = (zw.nplanes + zw.zchunks - 1) / zw.zchunks;
+    dim3 grid(((g.dx + 1) / 2 + BX - 1) / BX, (g.dy + BY - 1) / BY, (zw.nplanes + zchunk - 1) / zchunk);
+    wg_air_direct<BX, BY, FD, PF><<<grid, dim3(BX, BY), 0, w->stream>>>(
+            cur, prev, w->code.p, g, zchunk, zw.zbase, zw.nplanes, w->flag.p);
 }
 
-void launch_air(wvb_wg* w, const double* cur, double* prev) {
+void launch_air(wvb_wg* w, const double* cur, double* prev, ZWindow zw) {
+    if (zw.nplanes <= 0) return;
     if (w->variant == WVB_WG_KERNEL_TMA) {
-        with_tma_cfg(w, [&](auto cfg) { launch_tma<decltype(cfg)>(w, cur, prev); });
+        with_tma_cfg(w, [&](auto cfg) { launch_tma<decltype(cfg)>(w, cur, prev, zw); });
     } else if (w->fast_div) {
-        if (w->pf == 0) launch_direct_t<true, 0>(w, cur, prev);
-        else if (w->pf == 8) launch_direct_t<true, 8>(w, cur, prev);
-        else launch_direct_t<true, 4>(w, cur, prev);
+        if (w->pf == 0) launch_direct_t<true, 0>(w, cur, prev, zw);
+        else if (w->pf == 8) launch_direct_t<true, 8>(w, cur, prev, zw);
+        else launch_direct_t<true, 4>(w, cur, prev, zw);
     } else {
-        if (w->pf == 0) launch_direct_t<false, 0>(w, cur, prev);
-        else launch_direct_t<false, 4>(w, cur, prev);
+        if (w->pf == 0) launch_direct_t<false, 0>(w, cur, prev, zw);
+        else launch_direct_t<false, 4>(w, cur, prev, zw);
     }
     w->launches++;
+}
+void launch_air(wvb_wg* w, const double* cur, double* prev) {
+    launch_air(w, cur, prev, ZWindow{1, w->g.nzl, w->zchunks});
 }
 
 template <int THREADS, int MINB, bool PIPE>
@@ -353,20 +370,20 @@ void nccl_check(int r, const char* what) {
 }
 
 // one ghost-plane exchange of array `a` (both faces) with the z-neighbours
-void exchange_ghosts(wvb_wg* w, double* a) {
+void exchange_ghosts(wvb_wg* w, double* a, cudaStream_t st) {
     if (w->nranks <= 1) return;
     auto& n = nccl::get();
     const size_t cnt = (size_t)w->g.plane;
     nccl_check(n.GroupStart(), "ncclGroupStart");
     if (w->rank > 0) {
-        nccl_check(n.Send(a + cnt, cnt, nccl::t_float64, w->rank - 1, w->comm, w->stream), "ncclSend");
-        nccl_check(n.Recv(a, cnt, nccl::t_float64, w->rank - 1, w->comm, w->stream), "ncclRecv");
+        nccl_check(n.Send(a + cnt, cnt, nccl::t_float64, w->rank - 1, w->comm, st), "ncclSend");
+        nccl_check(n.Recv(a, cnt, nccl::t_float64, w->rank - 1, w->comm, st), "ncclRecv");
     }
     if (w->rank < w->nranks - 1) {
-        nccl_check(n.Send(a + cnt * w->g.nzl, cnt, nccl::t_float64, w->rank + 1, w->comm, w->stream),
+        nccl_check(n.Send(a + cnt * w->g.nzl, cnt, nccl::t_float64, w->rank + 1, w->comm, st),
                    "ncclSend");
         nccl_check(n.Recv(a + cnt * (w->g.nzl + 1), cnt, nccl::t_float64, w->rank + 1, w->comm,
-                          w->stream),
+                          st),
                    "ncclRecv");
     }
     nccl_check(n.GroupEnd(), "ncclGroupEnd");
@@ -378,6 +395,30 @@ void enqueue_launch(wvb_wg* w) {
     const double* cur = w->P[w->cur].p;
     double* prev = w->P[w->cur ^ 1].p;
     const bool has_boundary = w->bl[0].n + w->bl[1].n + w->bl[2].n;
+    if (w->nranks > 1 && w->overlap_comm && w->g.nzl >= 3) {
+        // Multi-GPU: the neighbours only need this slab's first and last owned plane. Those
+        // two planes (and the boundary lists, whose nodes lie on every plane) are updated
+        // first; their exchange then runs on its own stream underneath the update of the
+        // interior planes, which neither reads nor writes what is in flight.
+        const int nzl = w->g.nzl;
+        WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
+        if (has_boundary) {
+            WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
+            launch_boundary(w, cur, prev, w->stream_b);
+            WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
+        }
+        launch_air(w, cur, prev, ZWindow{1, 1, 1});
+        launch_air(w, cur, prev, ZWindow{nzl, 1, 1});
+        WVB_CUDA(cudaEventRecord(w->ev_faces, w->stream));
+        WVB_CUDA(cudaStreamWaitEvent(w->stream_c, w->ev_faces, 0));
+        if (has_boundary) WVB_CUDA(cudaStreamWaitEvent(w->stream_c, w->ev_join, 0));
+        exchange_ghosts(w, prev, w->stream_c);
+        WVB_CUDA(cudaEventRecord(w->ev_comm, w->stream_c));
+        launch_air(w, cur, prev, ZWindow{2, nzl - 2, w->zchunks_inner});
+        if (has_boundary) WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+        WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
+        return;
+    }
     if (w->overlap && has_boundary) {
         // the boundary lists and the air kernel write disjoint nodes of `prev`:
         // fork the boundary launch onto its own stream
@@ -396,7 +437,7 @@ void enqueue_launch(wvb_wg* w) {
         launch_air(w, cur, prev);
         launch_boundary(w, cur, prev, w->stream);
     }
-    exchange_ghosts(w, prev);
+    exchange_ghosts(w, prev, w->stream);
 }
 // launch + swap (waveguide.h:123)
 void enqueue_step(wvb_wg* w) {
@@ -572,6 +613,12 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaEventCreate(&w->ev1));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
+    WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_c, cudaStreamNonBlocking, prio_hi));
+    WVB_CUDA(cudaEventCreateWithFlags(&w->ev_faces, cudaEventDisableTiming));
+    WVB_CUDA(cudaEventCreateWithFlags(&w->ev_comm, cudaEventDisableTiming));
+    // measured neutral at N = 2 (0.5898 vs 0.5892 ms/step: the exchange costs ~13 us and the two
+    // extra launches + events about as much), so off by default; WVB_WG_OVERLAP_COMM=1 enables it
+    w->overlap_comm = env_int("WVB_WG_OVERLAP_COMM", 0);
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 4);
     w->bpipe = env_int("WVB_WG_BPIPE", 4);
@@ -635,6 +682,9 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     }
     const int zc_req = env_int("WVB_WG_ZCHUNKS", (int)((d->flags >> 16) & 0xfff));
     w->zchunks = zc_req > 0 ? std::min(zc_req, g.nzl) : pick_zchunks(tiles, g.nzl, slots, 12);
+    // the interior window [2, nzl) of the overlapped multi-GPU schedule
+    const int inner = std::max(1, g.nzl - 2);
+    w->zchunks_inner = zc_req > 0 ? std::min(zc_req, inner) : pick_zchunks(tiles, inner, slots, 12);
 
     // ---- NCCL ---------------------------------------------------------------------------
     if (w->nranks > 1) {
@@ -830,7 +880,7 @@ wvb_status wvb_wg_write_field(wvb_wg* w, const double* in) {
         WVB_CUDA(cudaSetDevice(w->dev));
         double* cur = w->P[w->cur].p;
         copy_field(w, cur, nullptr, in);
-        exchange_ghosts(w, cur);
+        exchange_ghosts(w, cur, w->stream);
         WVB_CUDA(cudaStreamSynchronize(w->stream));
     });
 }

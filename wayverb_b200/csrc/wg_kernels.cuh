@@ -167,11 +167,13 @@ __device__ __forceinline__ void update_pair(double l, double2 mid, double r, dou
 template <int BX, int BY, bool FAST_DIV, int PF>
 __global__ void __launch_bounds__(BX* BY)
 wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
-              const uint8_t* __restrict__ code, WgGeom g, int zchunk, int* __restrict__ flag) {
+              const uint8_t* __restrict__ code, WgGeom g, int zchunk, int zbase, int nplanes,
+              int* __restrict__ flag) {
+    // owned local planes [zbase, zbase + nplanes) (the whole slab: zbase = 1, nplanes = nzl)
     const int x0 = 2 * (blockIdx.x * BX + threadIdx.x);
     const int y = blockIdx.y * BY + threadIdx.y;
-    const int zs = 1 + blockIdx.z * zchunk;
-    const int ze = min(zs + zchunk, g.nzl + 1);
+    const int zs = zbase + blockIdx.z * zchunk;
+    const int ze = min(zs + zchunk, zbase + nplanes);
     int bad = 0;
     if (x0 < g.dx && y < g.dy && zs < ze) {
         const uint32_t sp = (uint32_t)g.plane;
@@ -315,7 +317,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ prev,
            const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y, int zchunks,
-           int* __restrict__ flag) {
+           int zbase, int nplanes, int* __restrict__ flag) {
     constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
     constexpr int R = Cfg::ROWS_PER_THREAD;
     extern __shared__ unsigned char smem_raw[];
@@ -351,8 +353,9 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
         const int x0 = tile_x * TX;
         const int y0 = tile_y * TY;
         // z range of this item: owned local planes [zs, ze); planes zs-1 .. ze are streamed
-        const int zs = 1 + (int)(((long long)g.nzl * chunk) / zchunks);
-        const int ze = 1 + (int)(((long long)g.nzl * (chunk + 1)) / zchunks);
+        // (of the window [zbase, zbase + nplanes): the whole slab is zbase = 1, nplanes = nzl)
+        const int zs = zbase + (int)(((long long)nplanes * chunk) / zchunks);
+        const int ze = zbase + (int)(((long long)nplanes * (chunk + 1)) / zchunks);
         const int n_planes = ze - zs + 2;
         // box origin in the padded array: column WG_XO + x0 - HX, row (y0 - 1) + 1
         const int bx = WG_XO + x0 - Cfg::HX, by = y0;
