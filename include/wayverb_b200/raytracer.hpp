@@ -56,13 +56,7 @@ struct alignas(32) surface final {
 struct alignas(8) triangle final {
     cl_uint surface, v0, v1, v2;
 };
-struct environment final {
-    double speed_of_sound{340.0};
-    double acoustic_impedance{400.0};
-};
-struct vec3 final {
-    float x, y, z;
-};
+// core::environment and core::vec3 live in waveguide.hpp (both paths use them)
 
 /// What core::scene_buffers uploads (scene_buffers.h:14-38), by reference.
 struct flattened_scene final {

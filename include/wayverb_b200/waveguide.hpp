@@ -66,6 +66,17 @@ struct value_is_inf final : public std::runtime_error {
 };
 }  // namespace exceptions
 
+/// core/environment.h:6-13
+struct environment final {
+    double speed_of_sound{340.0};
+    double acoustic_impedance{400.0};
+};
+constexpr double get_ambient_density(const environment& s) { return s.acoustic_impedance / s.speed_of_sound; }
+/// stands in for glm::vec3 in signatures
+struct vec3 final {
+    float x, y, z;
+};
+
 namespace detail {
 inline void check(wvb_status s) {
     if (s != WVB_OK && s != WVB_ERR_SIM) {
@@ -614,6 +625,22 @@ public:
         ret.pressure = pressure;
         return ret;
     }
+    /// the same evaluation from values gathered on the device: v[0] the node, v[1..6] its
+    /// neighbours in port order (fp64 device values, converted to cl_float like read_value does)
+    return_type from_gathered(const double* v) {
+        const auto pressure = cl_float(v[0]);
+        std::array<cl_float, 6> surrounding;
+        for (size_t i = 0; i != 6; ++i) surrounding[i] = cl_float((cl_float(v[1 + i]) - pressure) / mesh_spacing_);
+        const double m[3] = {(surrounding[1] - surrounding[0]) * 0.5, (surrounding[3] - surrounding[2]) * 0.5,
+                             (surrounding[5] - surrounding[4]) * 0.5};
+        output ret{};
+        for (int k = 0; k < 3; ++k) {
+            velocity_[k] -= m[k] / (ambient_density_ * sample_rate_);
+            ret.intensity[k] = float(velocity_[k] * double(pressure));
+        }
+        ret.pressure = pressure;
+        return ret;
+    }
     size_t get_output_node() const { return output_node_; }
 
 private:
@@ -626,6 +653,127 @@ private:
 };
 
 }  // namespace postprocessor
+
+// ---- canonical.h: the combination the engine drives -------------------------------------
+/// config.cpp:19-21 / mesh_descriptor.cpp:72-74
+inline double compute_sample_rate(const mesh_descriptor& d, double speed_of_sound) {
+    return 1 / (double(d.spacing) / (speed_of_sound * std::sqrt(3.0)));
+}
+/// mesh_descriptor.cpp:12-25: nearest node of a position (glm::round of float quotients)
+inline size_t compute_index(const mesh_descriptor& d, const core::vec3& pos) {
+    const float q[3] = {(pos.x - d.min_corner.s[0]) / d.spacing, (pos.y - d.min_corner.s[1]) / d.spacing,
+                        (pos.z - d.min_corner.s[2]) / d.spacing};
+    return compute_index(d, int(std::round(q[0])), int(std::round(q[1])), int(std::round(q[2])));
+}
+/// calibration.h:21-31
+inline double rectilinear_calibration_factor(double grid_spacing, double acoustic_impedance) {
+    return std::sqrt(acoustic_impedance / (4 * M_PI)) / (0.3405 * grid_spacing);
+}
+/// bandpass_band.h:11-20
+struct band final {
+    util::aligned::vector<postprocessor::directional_receiver::output> directional;
+    double sample_rate;
+};
+struct bandpass_band final {
+    struct band band;
+    struct {
+        double min, max;
+    } valid_hz;
+};
+/// Tag for "no per-step pressure callback": lets canonical_impl run the whole loop on the
+/// device (wvb_wg_run) and evaluate the directional receiver afterwards from the gathered
+/// pressures -- the same values, in the same order, as the per-step path.
+struct no_pressure_callback final {
+    template <typename Q, typename B>
+    void operator()(Q&, const B&, size_t, size_t) const {}
+};
+
+namespace detail {
+inline size_t checked_node(const mesh& mesh, const core::vec3& pt) {
+    const auto ret = compute_index(mesh.get_descriptor(), pt);
+    if (ret >= compute_num_nodes(mesh.get_descriptor()) || !is_inside(mesh, ret)) {
+        throw std::runtime_error{"Source/receiver node position appears to be outside mesh."};
+    }
+    return ret;
+}
+inline util::aligned::vector<float> canonical_input(const mesh& mesh, double ideal_steps,
+                                                    const core::environment& environment) {
+    auto raw = util::aligned::vector<float>(size_t(ideal_steps), 0.0f);
+    if (!raw.empty()) {
+        raw.front() = float(rectilinear_calibration_factor(mesh.get_descriptor().spacing,
+                                                           environment.acoustic_impedance));
+    }
+    return raw;
+}
+
+/// canonical.h:24-81
+template <typename Callback>
+bool canonical_impl(const core::compute_context& cc, const mesh& mesh, double simulation_time,
+                    const core::vec3& source, const core::vec3& receiver, const core::environment& environment,
+                    const std::atomic_bool& keep_going, Callback&& callback, band& out) {
+    const auto sample_rate = compute_sample_rate(mesh.get_descriptor(), environment.speed_of_sound);
+    const auto ideal_steps = std::ceil(sample_rate * simulation_time);
+    const auto input = canonical_input(mesh, ideal_steps, environment);
+    core::callback_accumulator<postprocessor::directional_receiver> output_accumulator{
+            mesh.get_descriptor(), sample_rate, core::get_ambient_density(environment),
+            checked_node(mesh, receiver)};
+    const auto steps = run(cc, mesh,
+                           preprocessor::make_hard_source(checked_node(mesh, source), input.begin(), input.end()),
+                           [&](auto& queue, const auto& buffer, auto step) {
+                               output_accumulator(queue, buffer, step);
+                               callback(queue, buffer, step, size_t(ideal_steps));
+                           },
+                           keep_going);
+    if (double(steps) != ideal_steps) return false;
+    out = band{std::move(output_accumulator.get_output()), sample_rate};
+    return true;
+}
+
+/// The same with nothing to call per step: one wvb_wg_run, receiver evaluated afterwards.
+inline bool canonical_impl(const core::compute_context& cc, const mesh& mesh, double simulation_time,
+                           const core::vec3& source, const core::vec3& receiver,
+                           const core::environment& environment, const std::atomic_bool& keep_going,
+                           no_pressure_callback, band& out) {
+    if (!keep_going) return false;
+    const auto sample_rate = compute_sample_rate(mesh.get_descriptor(), environment.speed_of_sound);
+    const auto ideal_steps = std::ceil(sample_rate * simulation_time);
+    const auto input = canonical_input(mesh, ideal_steps, environment);
+    const size_t rcv = checked_node(mesh, receiver);
+    postprocessor::directional_receiver dr{mesh.get_descriptor(), sample_rate,
+                                           core::get_ambient_density(environment), rcv};
+    util::aligned::vector<size_t> nodes{rcv};
+    for (auto n : compute_neighbors(mesh.get_descriptor(), rcv)) nodes.push_back(n);
+    const util::aligned::vector<double> signal(input.begin(), input.end());
+    util::aligned::vector<double> gathered;
+    const auto steps = run_stock(cc, mesh, checked_node(mesh, source), signal, false, nodes, gathered);
+    if (double(steps) != ideal_steps) return false;
+    out.sample_rate = sample_rate;
+    out.directional.clear();
+    out.directional.reserve(steps);
+    for (size_t s = 0; s < steps; ++s) out.directional.push_back(dr.from_gathered(&gathered[s * 7]));
+    return true;
+}
+}  // namespace detail
+
+/// canonical.h:85-110 (single band): hard source at the node nearest `source`, directional
+/// receiver at the node nearest `receiver`, `simulation_time` seconds. Empty on cancellation.
+template <typename PressureCallback>
+util::aligned::vector<bandpass_band> canonical(const core::compute_context& cc, const mesh& mesh,
+                                               const core::vec3& source, const core::vec3& receiver,
+                                               const core::environment& environment, double cutoff,
+                                               double simulation_time, const std::atomic_bool& keep_going,
+                                               PressureCallback&& pressure_callback) {
+    band b;
+    if (!detail::canonical_impl(cc, mesh, simulation_time, source, receiver, environment, keep_going,
+                                std::forward<PressureCallback>(pressure_callback), b)) {
+        return {};
+    }
+    util::aligned::vector<bandpass_band> ret(1);
+    ret[0].band = std::move(b);
+    ret[0].valid_hz.min = 0.0;
+    ret[0].valid_hz.max = cutoff;
+    return ret;
+}
 
 }  // namespace waveguide
 }  // namespace wayverb

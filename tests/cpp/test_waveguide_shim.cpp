@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -41,11 +42,54 @@ static int gaussian_directional(int steps, double b0) {
     return 0;
 }
 
+// canonical.h:24-110: hard source with the calibrated unit impulse, directional receiver,
+// simulation_time seconds -- once through the per-step callback path, once with nothing to
+// call per step (one wvb_wg_run); both must give the same samples. Prints them.
+static int canonical_run(double b0) {
+    const compute_context cc{};
+    coefficients_canonical c{};
+    c.b[0] = b0;
+    c.a[0] = 1.0;
+    auto m = make_cuboid_mesh(28, 26, 24, 0.05f, c);
+    const core::environment env{};
+    const core::vec3 source{0.52f, 0.61f, 0.48f}, receiver{0.86f, 0.59f, 0.51f};
+    const double sr = compute_sample_rate(m.get_descriptor(), env.speed_of_sound);
+    const double seconds = 120.2 / sr;  // ceil -> 121 steps
+    size_t calls = 0, total_seen = 0;
+    const auto a = canonical(cc, m, source, receiver, env, 500.0, seconds, true,
+                             [&](auto&, const auto&, auto step, auto total) {
+                                 calls += (step == calls);
+                                 total_seen = total;
+                             });
+    const auto b = canonical(cc, m, source, receiver, env, 500.0, seconds, true, no_pressure_callback{});
+    if (a.size() != 1 || b.size() != 1) return 9;
+    if (calls != 121 || total_seen != 121) return 10;
+    const auto& x = a[0].band.directional;
+    const auto& y = b[0].band.directional;
+    if (x.size() != 121 || y.size() != 121 || a[0].band.sample_rate != sr || a[0].valid_hz.max != 500.0) return 11;
+    for (size_t i = 0; i < x.size(); ++i) {
+        if (std::memcmp(&x[i], &y[i], sizeof x[i])) return 12;  // callback path == device path
+        std::printf("%.9g %.9g %.9g %.9g\n", x[i].pressure, x[i].intensity[0], x[i].intensity[1], x[i].intensity[2]);
+    }
+    std::printf("# source %zu receiver %zu input %.9g\n", compute_index(m.get_descriptor(), source),
+                compute_index(m.get_descriptor(), receiver),
+                float(rectilinear_calibration_factor(m.get_descriptor().spacing, env.acoustic_impedance)));
+    try {  // a position outside the mesh
+        canonical(cc, m, core::vec3{-5, 0, 0}, receiver, env, 500.0, seconds, true, no_pressure_callback{});
+        return 13;
+    } catch (const std::runtime_error&) {
+    }
+    std::atomic_bool stop{false};
+    if (!canonical(cc, m, source, receiver, env, 500.0, seconds, stop, no_pressure_callback{}).empty()) return 14;
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 60;
     if (argc > 3 && std::string(argv[3]) == "gaussian") {
         return gaussian_directional(steps, strtod(argv[2], nullptr));
     }
+    if (argc > 3 && std::string(argv[3]) == "canonical") return canonical_run(strtod(argv[2], nullptr));
     const compute_context cc{};
     coefficients_canonical c{};
     c.b[0] = argc > 2 ? strtod(argv[2], nullptr) : 39.0;  // impedance b0 of a flat surface

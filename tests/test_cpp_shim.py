@@ -101,6 +101,39 @@ def test_gaussian_preprocessor_and_directional_receiver(tmp_path):
 
 
 @pytest.mark.gpu
+def test_canonical_single_band_matches_oracle(tmp_path):
+    """waveguide::canonical (canonical.h:24-110) through the shim -- per-step callback path and
+    the one-call device path, which the executable checks are identical -- against the oracle:
+    calibrated unit impulse as a hard source, pressure at the receiver node read as float."""
+    exe = build(tmp_path, "test_waveguide_shim")
+    c = wgo.to_flat(0.2)
+    r = subprocess.run([exe, "0", "%.17g" % c["b"][0], "canonical"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr)
+    lines = r.stdout.strip().splitlines()
+    got = np.array([[float(v) for v in line.split()] for line in lines if not line.startswith("#")])
+    meta = [line for line in lines if line.startswith("#")][0].split()
+    src, rcv, amp = int(meta[2]), int(meta[4]), float(meta[6])
+    dims = (28, 26, 24)
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [c])
+    # compute_index(descriptor, position): round((p - min_corner) / spacing) in float
+    sp = np.float32(0.05)
+    loc = lambda p: [int(np.round(np.float32(v) / sp)) for v in p]  # noqa: E731
+    assert src == om.index(*loc((0.52, 0.61, 0.48))) and rcv == om.index(*loc((0.86, 0.59, 0.51)))
+    # rectilinear_calibration_factor (calibration.h:21-31), stored as float (canonical.h:48-56)
+    want_amp = np.float32(np.sqrt(400.0 / (4 * np.pi)) / (0.3405 * np.float64(sp)))
+    assert amp == pytest.approx(float(want_amp), rel=1e-7)
+    steps = got.shape[0]
+    assert steps == 121
+    sig = np.zeros(steps)
+    sig[0] = float(want_amp)
+    done, want, flag = wgo.Sim(om).run(src, sig, [rcv], soft=False)
+    assert done == steps and flag == 0
+    # printed with 9 significant digits from a float: compare as float32
+    assert np.array_equal(got[:, 0].astype(np.float32), want[:, 0].astype(np.float32))
+    assert np.abs(got[:, 1:]).max() > 0
+
+
+@pytest.mark.gpu
 def test_raytracer_run_template(tmp_path):
     exe = build(tmp_path, "test_raytracer_shim")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
