@@ -73,7 +73,7 @@ def test_ray_handle_with_nothing_to_do():
         assert refl is None and dropped == 0 and np.count_nonzero(g.histogram()) == 0
         refl, _, _ = g.trace(rto.directions(1, 7), src, rcv, depth=0, n_bins=50, keep_steps=0)
         assert np.count_nonzero(g.histogram()) == 0  # depth 0: no reflection, nothing deposited
-        with wvb.ImageSource(g, src, rcv, max_elements=10) as s:
+        with wvb.ImageSource(g, src, rcv, max_elements=16) as s:
             got, stats, _ = s.results()  # nothing pushed: the direct impulse alone
             want, _ = rto.image_source(rto.Scene(sc), np.zeros((1, 0), np.uint32), src, rcv)
             assert got.size == want.size == 1 and np.array_equal(got.view(np.uint8), want.view(np.uint8))
