@@ -522,7 +522,9 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     g.dx = dx; g.dy = dy; g.nzl = d->z_end - d->z_begin;
     g.px = (dx + WG_XO + 2 + 3) & ~3;  // zero border: WG_XO columns left, >= 2 right
     g.py = dy + 2;                     // zero rows above and below
-    g.pc = (dx + 1 + 15) & ~15;        // class bytes: >= 1 "do not write" column right of the row
+    // class codes: one byte per x-adjacent node PAIR (node 2k in the low nibble), rows padded
+    // with >= 1 "do not write" pair
+    g.pc = ((dx + 1) / 2 + 1 + 15) & ~15;
     g.plane = (long long)g.px * g.py;
     g.cplane = (long long)g.pc * dy;
     const long long total = g.plane * (g.nzl + 2);
@@ -530,7 +532,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
 
     // ---- digest the nodes: class bytes + boundary lists (node order) ----------
     const node_view nv{d->nodes, d->nodes_z0, d->nodes_nz, dx, dy, dz};
-    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), CLS_BOUNDARY);
+    std::vector<uint8_t> code((size_t)g.cplane * (g.nzl + 2), (uint8_t)(CLS_BOUNDARY | (CLS_BOUNDARY << 4)));
     std::vector<std::array<uint32_t, 3>> plane_counts(g.nzl);
     std::vector<uint64_t> plane_air(g.nzl, 0);
     parallel_for(g.nzl, [&](int64_t lp) {
@@ -542,7 +544,8 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
             for (int x = 0; x < dx; ++x) {
                 int nd;
                 const int cls = node_class(nv.type_at(x, y, z), &nd);
-                crow[(size_t)y * g.pc + x] = (uint8_t)cls;
+                uint8_t& cb = crow[(size_t)y * g.pc + (x >> 1)];
+                cb = (x & 1) ? (uint8_t)((cb & 0x0f) | (cls << 4)) : (uint8_t)((cb & 0xf0) | cls);
                 if (cls == CLS_BOUNDARY) c[nd - 1]++;
                 if (cls == CLS_AIR) air++;
             }

@@ -26,8 +26,9 @@
 //          (program.cpp:402-407) needs no bounds test. Node (x, y, local plane
 //          lz) lives at ((lz*(dy+2) + y+1)*px + WG_XO + x); WG_XO = 4 and px a
 //          multiple of 4 keep node pairs 16-byte and rows 32-byte aligned.
-//   code   u8 node class, (nzl+2) x dy x pc bytes (no border); columns >= dx of
-//          a row are CLS_BOUNDARY ("do not write").
+//   code   node classes, one byte per x-adjacent node pair (node 2k in the low nibble),
+//          (nzl+2) x dy x pc bytes (no border); pairs right of the row are
+//          CLS_BOUNDARY ("do not write").
 //   lists  per boundary class N: off[n] (element offset into P), meta[n],
 //          ci[N][n] coefficient indices, mem[N][6][n] filter memory.
 #pragma once
@@ -124,7 +125,7 @@ __device__ __forceinline__ void raise_flags(int bad, int* flag) {
 // The update of one x-adjacent node pair (normal_waveguide_update,
 // program.cpp:393-412, for both nodes). Port order nx, px, ny, py, nz, pz; the
 // leading `0 +` of the reference is the first operand itself. `ck` holds the two
-// class bytes. Writes the result(s) to dst unless the class says BOUNDARY.
+// classes (low / high nibble). Writes the result(s) to dst unless the class says BOUNDARY.
 template <bool FAST_DIV>
 __device__ __forceinline__ void update_pair(double l, double2 mid, double r, double2 u, double2 d,
                                             double2 below, double2 above, double2 p, unsigned ck,
@@ -139,7 +140,7 @@ __device__ __forceinline__ void update_pair(double l, double2 mid, double r, dou
         v0 = s0 / 3.0 - p.x;
         v1 = s1 / 3.0 - p.y;
     }
-    const unsigned c0 = ck & 0xffu, c1 = ck >> 8;
+    const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
     if (c0 != CLS_AIR) v0 = 0.0;
     if (c1 != CLS_AIR) v1 = 0.0;
     if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {  // rare: inf / nan
@@ -180,12 +181,12 @@ wg_air_direct(const double* __restrict__ cur, double* __restrict__ prev,
         const uint32_t row = (uint32_t)g.px;
         const uint32_t ksp = (uint32_t)g.cplane;
         uint32_t off = (uint32_t)wg_offset(g, x0, y, zs);
-        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y) * g.pc + x0);
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y) * g.pc + (x0 >> 1));
         int z = zs;
         auto iter = [&](const double2& below, const double2& mid, double2& above) {
             above = ld2(cur + (off + sp));
             const double2 p = ld2(prev + off);
-            const unsigned ck = *reinterpret_cast<const unsigned short*>(code + koff);
+            const unsigned ck = code[koff];
             if (PF > 0 && z + PF <= g.nzl) {
                 prefetch_l2(cur + (off + (PF + 1) * sp));
                 prefetch_l2(prev + (off + PF * sp));
@@ -376,17 +377,17 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) valid[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
         uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, zs);  // row rr: + 4 rr px
-        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + x);
+        uint32_t koff = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + (x >> 1));
 
         double2 p_next[R];
         unsigned c_next[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             p_next[rr] = make_double2(0.0, 0.0);
-            c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 8);
+            c_next[rr] = CLS_BOUNDARY | (CLS_BOUNDARY << 4);
             if (valid[rr]) {
                 p_next[rr] = ld2(prev + (off + rr * rstep));
-                c_next[rr] = *reinterpret_cast<const unsigned short*>(code + (koff + rr * krstep));
+                c_next[rr] = code[koff + rr * krstep];
             }
         }
 
@@ -417,8 +418,7 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
                 for (int rr = 0; rr < R; ++rr) {
                     if (valid[rr]) {
                         p_next[rr] = ld2(prev + (off + sp + rr * rstep));
-                        c_next[rr] = *reinterpret_cast<const unsigned short*>(
-                                code + (koff + ksp + rr * krstep));
+                        c_next[rr] = code[koff + ksp + rr * krstep];
                     }
                 }
             }
