@@ -418,7 +418,8 @@ wvb_status wvb_is_push_reflections(wvb_is* is, const wvb_reflection* reflections
                                    uint32_t steps, uint64_t ray_index_base);
 /* raytracer::run for n_rays (wvb_rt_trace) with the first `order` reflections handed
  * to the tree on the device: no reflection has to leave the GPU. reflections
- * (optional): [params->keep_steps][n_rays] records for other, host-side consumers. */
+ * (optional): [params->keep_steps][n_rays] records for other, host-side consumers.
+ * dropped: as in wvb_rt_trace. device_ms is not measured here (0). */
 wvb_status wvb_is_trace(wvb_is* is, const wvb_rt_trace_params* params, const float* directions,
                         uint64_t n_rays, uint32_t order, wvb_reflection* reflections, uint64_t* dropped,
                         float* device_ms);

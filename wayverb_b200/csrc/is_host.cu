@@ -22,6 +22,7 @@ using namespace wvb;
 // defined in rt_host.cu
 extern "C++" const rt::Scene* wvb_rt_device_scene(const wvb_rt* r, int* device);
 extern "C++" cudaStream_t wvb_rt_stream(const wvb_rt* r);
+extern "C++" const unsigned long long* wvb_rt_dropped_counter(const wvb_rt* r);
 extern "C++" void wvb_rt_trace_enqueue(wvb_rt* r, const wvb_rt_trace_params* p, const float* directions,
                                        uint32_t n, rt::ReflectionPod* d_refl, uint32_t keep);
 
@@ -199,8 +200,10 @@ wvb_status wvb_is_trace(wvb_is* s, const wvb_rt_trace_params* p, const float* di
             WVB_CUDA(cudaMemcpyAsync(reflections, d.p, (size_t)to_host * n * 32, cudaMemcpyDeviceToHost,
                                      s->stream));
         }
+        unsigned long long dr = 0;
+        WVB_CUDA(cudaMemcpyAsync(&dr, wvb_rt_dropped_counter(s->scene), 8, cudaMemcpyDeviceToHost, s->stream));
         WVB_CUDA(cudaStreamSynchronize(s->stream));
-        if (dropped) *dropped = 0;  // the histogram's drop counter stays with the scene handle
+        if (dropped) *dropped = dr;  // as wvb_rt_trace reports it
         if (device_ms) *device_ms = 0;
     });
 }

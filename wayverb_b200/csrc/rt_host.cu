@@ -85,6 +85,8 @@ const rt::Scene* wvb_rt_device_scene(const wvb_rt* r, int* device) {
 }
 
 cudaStream_t wvb_rt_stream(const wvb_rt* r) { return r->stream; }
+// the histogram's drop counter (impulses beyond n_bins), device resident
+const unsigned long long* wvb_rt_dropped_counter(const wvb_rt* r) { return r->dropped.p; }
 
 // Enqueues one trace of n rays on the handle's stream (no synchronisation):
 // directions from the host or generated, the rt_trace launch bracketed by the
