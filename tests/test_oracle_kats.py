@@ -263,3 +263,55 @@ def test_error_flags():
     nodes["boundary_index"][m.index(0, 5, 5)] = 0
     bad = wgo.Mesh(m.dims, nodes, m.coeffs, m.b1, m.b2, m.b3)
     assert wgo.Sim(bad).step(1) & wgo.ERR_OUTSIDE_MESH
+
+
+# ---- the reference's transparent-source identity (SURVEY 8c KAT 1) ---------------------
+def _mesh_impulse_response(n):
+    """write_compensation_signal (compensation_signal/cmd/main.cpp:33-47, lib/.../waveguide.h:53-115):
+    a free-field mesh, float pressures, hard source {0, 1, 0, 0, ...} at the centre node (a hard
+    source keeps pinning the node to its next sample, zeros included), output = that node after
+    every step. The reference folds the mesh into a 1/48 wedge; a cube too large for any
+    reflection to return within n steps gives the same values."""
+    half = n // 2 + 3
+    d = 2 * half + 5
+    inside = np.zeros((d, d, d), bool)
+    inside[2:-2, 2:-2, 2:-2] = True
+    m = wgo.mesh_from_inside(inside, [wgo.to_flat(0.1)])
+    c = m.index(d // 2, d // 2, d // 2)
+    sim = wgo.Sim(m, real="float")
+    out = np.zeros(n)
+    for k in range(n):
+        sim.write(c, 1.0 if k == 1 else 0.0)   # the writer runs before the kernel ...
+        assert sim.step(1) == 0
+        out[k] = sim.read(c)                   # ... and the output is read after the swap
+    return out
+
+
+def test_transparent_soft_source_reproduces_its_input():
+    """src/waveguide/tests/waveguide_init.cpp:18-63: a soft source fed make_transparent(input)
+    (make_transparent.cpp:10-33: input minus its convolution with the right-Hanning-windowed mesh
+    impulse response) leaves exactly `input` at the source node -- within 1e-4 for the first
+    input.size() steps, in a 2 m box of absorption 0.001 meshed at 0.04 m."""
+    steps, n_ir = 100, 512
+    ir = np.zeros(n_ir)
+    ir[:steps + 4] = _mesh_impulse_response(steps + 4)  # later samples cannot act within `steps`
+    window = 0.5 - 0.5 * np.cos(2 * np.pi * (0.5 + np.arange(n_ir) / (2 * (n_ir - 1.0))))  # right_hanning
+    windowed = (window * ir).astype(np.float32)
+    x = np.ones(20, np.float32)
+    conv = np.convolve(x.astype(np.float64), windowed.astype(np.float64))
+    transparent = -conv
+    transparent[:x.size] += x
+    transparent = transparent[:steps].astype(np.float32).astype(np.float64)
+    # geo::box(-1, 1), spacing 0.04, two layers of padding each side like compute_adjusted_boundary
+    side = int(round(2.0 / 0.04)) + 1 + 4
+    inside = np.zeros((side, side, side), bool)
+    inside[2:-2, 2:-2, 2:-2] = True
+    m = wgo.mesh_from_inside(inside, [wgo.to_flat(0.001)])
+    c = m.index(side // 2, side // 2, side // 2)
+    for real in ("float", "double"):
+        done, out, flag = wgo.Sim(m, real=real).run(c, transparent, [c], soft=True)
+        assert done == steps and flag == 0
+        assert np.abs(out[:x.size, 0] - x).max() < 1e-4, real
+        # and it is the compensation that does it: the plain soft source rings
+        _, plain, _ = wgo.Sim(m, real=real).run(c, np.r_[x, np.zeros(steps - x.size)], [c], soft=True)
+        assert np.abs(plain[:x.size, 0] - x).max() > 0.1
