@@ -61,7 +61,6 @@ def test_division_by_three_is_correctly_rounded():
     """The kernels divide by 3 with an FMA-corrected reciprocal multiply
     (csrc/wg_kernels.cuh third<true>); it must equal the IEEE division bit for
     bit, including specials, the denormal range and adversarial significands."""
-    import ctypes as C
     rng = np.random.default_rng(11)
     n = 1 << 24
     bits = rng.integers(0, 1 << 52, n, dtype=np.uint64)

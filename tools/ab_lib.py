@@ -2,7 +2,6 @@
 alternates the libraries in fresh processes and prints the step time of each.
 usage: ab_lib.py A B [C ...] [rounds]   where each arm is a library path or a
 comma-separated list of environment settings (WVB_WG_BPIPE=4,WVB_WG_BMINB=4)."""
-import json
 import os
 import subprocess
 import sys

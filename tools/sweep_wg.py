@@ -1,7 +1,6 @@
 """Times the waveguide step for kernel variants / tile parameters on one GPU.
 Development tool (not the bench): prints Mnode-updates/s and the 32 B/node
 bandwidth figure for each configuration."""
-import itertools
 import json
 import os
 import sys

@@ -14,7 +14,7 @@ write_value on the `current` buffer (core/cl/common.h:42-57).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Optional, Sequence
+from typing import Callable, Optional
 
 import numpy as np
 
