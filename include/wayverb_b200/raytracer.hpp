@@ -27,6 +27,7 @@
 #include <atomic>
 #include <cmath>
 #include <experimental/optional>
+#include <limits>
 #include <random>
 #include <type_traits>
 #include <cstring>
@@ -712,6 +713,22 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
     }
     return std::experimental::make_optional(detail::collect_results(processors, seq));
 }
+
+
+/// image_source/run.h:12-47: raytracer::run with only the image-source processor, every
+/// reflection step eligible (max order = the reflection depth).
+namespace image_source {
+template <typename It>
+auto run(It b, It e, const core::compute_context& cc, const core::flattened_scene& voxelised,
+         const core::vec3& source, const core::vec3& receiver, const core::environment& environment,
+         uint64_t seed = std::random_device{}()) {
+    const auto callbacks = std::make_tuple(reflection_processor::make_image_source{std::numeric_limits<size_t>::max()});
+    auto results = raytracer::run(b, e, cc, voxelised, source, receiver, environment, true,
+                                  [](auto /*i*/, auto /*steps*/) {}, callbacks, seed);
+    if (!results) throw std::runtime_error{"Raytracer failed to generate results."};
+    return std::move(std::get<0>(*results));
+}
+}  // namespace image_source
 
 }  // namespace raytracer
 }  // namespace wayverb

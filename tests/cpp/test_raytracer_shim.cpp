@@ -157,6 +157,12 @@ int main(int argc, char** argv) {
         }
         std::printf("IMAGE_SOURCES %zu\n", imps.size());
     }
+    if (argc > 5) {  // image_source::run (image_source/run.h:12-47): compile check only; the same calls with
+                     // order = depth run through the C ABI in tests/test_is_gpu.py (exact shoebox KAT)
+        const auto imps = raytracer::image_source::run(dirs.begin(), dirs.begin() + 100, cc, scene, source, receiver,
+                                                       core::environment{}, 1);
+        std::printf("%zu\n", imps.size());
+    }
     std::printf("RT_SHIM_OK energy=%g bins=%zu\n", total, res.histogram.histogram.size());
     return 0;
 }
