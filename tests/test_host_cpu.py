@@ -40,6 +40,25 @@ def test_library_exports_every_declared_symbol():
 def test_pod_layouts():
     assert _lib.NODE_DT.itemsize == 8 and _lib.COEFF_DT.itemsize == 112 and _lib.BDATA_DT.itemsize == 56
     assert C.sizeof(_lib.WgRunParams) == 56
+    # wvb_is_desc: 2 x float[3], double, 2 x int32, uint64; raytracer::impulse<8> is 64 bytes
+    assert C.sizeof(_lib.IsDesc) == 48 and _lib.IsDesc.acoustic_impedance.offset == 24
+    assert _lib.IMPULSE_DT.itemsize == 64 and _lib.IMPULSE_DT.fields["distance"][1] == 48
+
+
+def test_header_struct_sizes_with_the_c_compiler(tmp_path):
+    """the ctypes mirrors against the header itself: compile a C program that prints sizeof"""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "wvb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(wvb_is_desc), sizeof(wvb_impulse), sizeof(wvb_rt_trace_params), sizeof(wvb_wg_run_params),'
+                   'sizeof(wvb_coefficients_canonical), sizeof(wvb_reflection), sizeof(wvb_condensed_node));return 0;}\n')
+    exe = tmp_path / "sizes"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(src)],
+                   check=True)  # the header is plain C
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(_lib.IsDesc), _lib.IMPULSE_DT.itemsize, C.sizeof(_lib.RtTraceParams),
+                   C.sizeof(_lib.WgRunParams), _lib.COEFF_DT.itemsize, 32, _lib.NODE_DT.itemsize]
 
 
 @pytest.mark.parametrize("dims", [(14, 12, 10), (5, 5, 5), (9, 6, 7), (33, 27, 22)])
