@@ -665,6 +665,11 @@ inline size_t compute_index(const mesh_descriptor& d, const core::vec3& pos) {
                         (pos.z - d.min_corner.s[2]) / d.spacing};
     return compute_index(d, int(std::round(q[0])), int(std::round(q[1])), int(std::round(q[2])));
 }
+/// mesh_descriptor.cpp:27-30
+inline core::vec3 compute_position(const mesh_descriptor& d, const std::array<int, 3>& locator) {
+    return {d.min_corner.s[0] + float(locator[0]) * d.spacing, d.min_corner.s[1] + float(locator[1]) * d.spacing,
+            d.min_corner.s[2] + float(locator[2]) * d.spacing};
+}
 /// calibration.h:21-31
 inline double rectilinear_calibration_factor(double grid_spacing, double acoustic_impedance) {
     return std::sqrt(acoustic_impedance / (4 * M_PI)) / (0.3405 * grid_spacing);
