@@ -1,0 +1,310 @@
+"""ctypes front-end of oracle/_ref/lib_ref.so: the REFERENCE'S OWN OpenCL-C kernels, extracted
+from /root/reference at build time and compiled for the host by oracle/ref_recipe/build.py.
+
+TEST INFRASTRUCTURE ONLY (tests/ and bench.py's reference arm). It exists to pin the oracle
+(oracle/wg_oracle.cpp, oracle/rt_oracle.cpp) to reference-run output; the product never loads it.
+
+Host loops of the reference that are C++ templates over OpenCL handles (waveguide.h:36-126,
+reflector.cpp:31-51, stochastic/finder.h:48-79, stochastic_histogram.h:70-111) cannot be
+compiled here; they are driven from this file in the order the reference drives them, each
+step citing its line.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("_wvb_ref_recipe", os.path.join(_HERE, "ref_recipe", "build.py"))
+recipe = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(recipe)
+
+NODE_DT = np.dtype([("boundary_type", "<i4"), ("boundary_index", "<u4")])
+COEFF_DT = np.dtype([("b", "<f8", (7,)), ("a", "<f8", (7,))])
+BDATA_DT = np.dtype([("mem", "<f8", (6,)), ("coefficient_index", "<u4"), ("pad", "<u4")])
+REFL_DT = np.dtype([("position", "<f4", (4,)), ("triangle", "<u4"), ("keep_going", "i1"),
+                    ("receiver_visible", "i1"), ("pad", "i1", (10,))])
+RAY_DT = np.dtype([("position", "<f4", (4,)), ("direction", "<f4", (4,))])
+IMPULSE_DT = np.dtype([("volume", "<f4", (8,)), ("position", "<f4", (4,)), ("distance", "<f4"),
+                       ("pad", "<f4", (3,))])
+
+_lib = None
+
+
+def available() -> bool:
+    return recipe.build() is not None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = recipe.build()
+        if path is None:
+            raise RuntimeError("oracle/_ref/lib_ref.so is absent and /root/reference is not here to build it")
+        L = C.CDLL(path)
+        vp, sz, i, u, f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
+        for p in ("f32_", "f64_"):
+            g = lambda n: getattr(L, "refk_" + p + n)  # noqa: E731
+            g("wg_step").restype = i
+            g("wg_step").argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, sz]
+            g("filter_test").argtypes = [vp, vp, vp, vp, sz]
+            g("filter_test_2").argtypes = [vp, vp, vp, vp, sz]
+            g("to_locator").argtypes = [sz, i, i, i, vp]
+            g("neighbor_index").restype = u
+            g("neighbor_index").argtypes = [i, i, i, i, i, i, i]
+            for n in ("sizeof_real", "sizeof_boundary_data", "sizeof_coefficients", "sizeof_node"):
+                g(n).restype = sz
+        assert L.refk_f32_sizeof_real() == 4 and L.refk_f64_sizeof_real() == 8
+        assert L.refk_f32_sizeof_boundary_data() == BDATA_DT.itemsize == 56
+        assert L.refk_f32_sizeof_coefficients() == COEFF_DT.itemsize == 112
+        assert L.refk_f32_sizeof_node() == NODE_DT.itemsize == 8
+        L.refk_init_reflections.argtypes = [vp, sz]
+        L.refk_reflections.argtypes = [vp, vp, vp, vp, u, vp, vp, vp, vp, vp, sz]
+        L.refk_triangle_vert_intersection.argtypes = [vp, vp, vp]
+        L.refk_closest_hit.argtypes = [vp, sz, i, vp, vp, u, vp, u, vp, vp, vp]
+        L.refk_sphere_point.argtypes = [f, f, vp]
+        L.refk_init_stochastic_path_info.argtypes = [vp, f, vp, sz]
+        L.refk_stochastic.argtypes = [vp, vp, f, vp, vp, vp, vp, vp, vp, sz]
+        L.refk_set_node_inside.argtypes = [vp, vp, vp, f, vp, vp, u, vp, vp, sz]
+        L.refk_set_node_boundary_type.argtypes = [vp, vp, vp, f, sz]
+        L.refk_boundary_coefficient_finder_1d.argtypes = [vp, vp, vp, f, vp, vp, vp, u, vp, u, vp, sz, i]
+        L.refk_boundary_coefficient_finder_2d.argtypes = [vp, vp, vp, f, vp, vp, sz]
+        L.refk_boundary_coefficient_finder_3d.argtypes = [vp, vp, vp, f, vp, vp, sz]
+        for n, want in (("reflection", 32), ("ray", 32), ("surface", 64), ("triangle", 16), ("impulse", 64),
+                        ("path_info", 64), ("mesh_descriptor", 48)):
+            fn = getattr(L, "refk_sizeof_" + n)
+            fn.restype = sz
+            assert fn() == want, (n, fn())
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- waveguide --------------------------------------------------------------------------
+class Sim:
+    """waveguide::run's state and step (waveguide.h:43-124) around the reference's
+    condensed_waveguide kernel. real="float": the reference's own types (float pressures,
+    double filters); real="double": the same source built with float -> double."""
+
+    def __init__(self, mesh, real="float"):
+        self.mesh = mesh
+        self.p = {"float": "f32_", "double": "f64_"}[real]
+        self.dtype = np.float32 if real == "float" else np.float64
+        n = mesh.num_nodes
+        # waveguide.h:47-56 two zeroed pressure buffers
+        self.prev = np.zeros(n, self.dtype)
+        self.cur = np.zeros(n, self.dtype)
+        self.nodes = np.ascontiguousarray(mesh.nodes, NODE_DT)
+        self.coeffs = np.ascontiguousarray(mesh.coeffs, COEFF_DT)
+        # setup.h:68-85 get_boundary_data<n>: zero filter memory, coefficient_index copied
+        self.bd = []
+        for b in (mesh.b1, mesh.b2, mesh.b3):
+            a = np.zeros((max(b.shape[0], 1), b.shape[1]), BDATA_DT)
+            if b.shape[0]:
+                a["coefficient_index"][:b.shape[0]] = b
+            self.bd.append(a)
+        self._n = [mesh.b1.shape[0], mesh.b2.shape[0], mesh.b3.shape[0]]
+
+    def write(self, node, v):
+        self.cur[int(node)] = v
+
+    def read(self, node):
+        return float(self.cur[int(node)])
+
+    def field(self):
+        return self.cur.astype(np.float64)
+
+    def set_field(self, f):
+        self.cur[:] = np.asarray(f, np.float64).reshape(-1)
+
+    def step(self, n=1) -> int:
+        dx, dy, dz = self.mesh.dims
+        fn = getattr(lib(), "refk_" + self.p + "wg_step")
+        flags = 0
+        for _ in range(int(n)):
+            # waveguide.h:82-97 flag reset + kernel, :123 swap
+            flags |= fn(_p(self.prev), _p(self.cur), _p(self.nodes), dx, dy, dz,
+                        _p(self.bd[0]), _p(self.bd[1]), _p(self.bd[2]), _p(self.coeffs), self.mesh.num_nodes)
+            self.prev, self.cur = self.cur, self.prev
+        return flags
+
+    def run(self, src_node, signal, rcv_nodes, soft=False):
+        """waveguide::run with hard_source / soft_source (preprocessor/*.h:17-25) and
+        postprocessor::node (node.cpp:14-18). Stops at the first error flag like
+        waveguide.h:100-119 throws."""
+        out = np.zeros((len(signal), len(rcv_nodes)))
+        for s, x in enumerate(signal):
+            if soft:
+                self.cur[src_node] = self.dtype(self.cur[src_node] + self.dtype(x))
+            else:
+                self.cur[src_node] = x
+            # the reference enqueues the kernel, then `post` reads `current` (waveguide.h:85-121)
+            for k, r in enumerate(rcv_nodes):
+                out[s, k] = self.cur[int(r)]
+            flag = self.step(1)
+            if flag:
+                return s, out, flag
+        return len(signal), out, 0
+
+    def boundary_data(self, n):
+        return self.bd[n - 1][:self._n[n - 1]]
+
+
+def filter_biquads(biquads, x_f32, real="float"):
+    """filter_test (cl/filters.cpp:56-65) on one stream, sample by sample."""
+    p = {"float": "f32_", "double": "f64_"}[real]
+    dt = np.float32 if real == "float" else np.float64
+    c = np.ascontiguousarray(biquads, np.float64).reshape(3, 6).copy()  # 3 x {b[3], a[3]}
+    m = np.zeros(6)
+    x = np.ascontiguousarray(x_f32, dt)
+    y = np.zeros_like(x)
+    fn = getattr(lib(), "refk_" + p + "filter_test")
+    for i in range(x.size):
+        fn(_p(x[i:i + 1]), _p(y[i:i + 1]), _p(m), _p(c), 1)
+    return y
+
+
+def filter_canonical(coeffs, x, real="float"):
+    """filter_test_2 (cl/filters.cpp:67-75) on one stream."""
+    p = {"float": "f32_", "double": "f64_"}[real]
+    dt = np.float32 if real == "float" else np.float64
+    c = np.ascontiguousarray(coeffs, COEFF_DT).reshape(1).copy()
+    m = np.zeros(6)
+    xx = np.ascontiguousarray(x, dt)
+    y = np.zeros_like(xx)
+    fn = getattr(lib(), "refk_" + p + "filter_test_2")
+    for i in range(xx.size):
+        fn(_p(xx[i:i + 1]), _p(y[i:i + 1]), _p(m), _p(c), 1)
+    return y
+
+
+def to_locator(index, dims):
+    out = np.zeros(3, np.int32)
+    lib().refk_f32_to_locator(int(index), int(dims[0]), int(dims[1]), int(dims[2]), _p(out))
+    return tuple(int(v) for v in out)
+
+
+def neighbor_index(loc, dims, port):
+    return int(lib().refk_f32_neighbor_index(int(loc[0]), int(loc[1]), int(loc[2]),
+                                             int(dims[0]), int(dims[1]), int(dims[2]), int(port)))
+
+
+# ---- rays -------------------------------------------------------------------------------------
+class RayScene:
+    """Holds the flattened scene arrays (core/spatial_division/scene_buffers.h:14-38)."""
+
+    def __init__(self, sc):
+        self.voxel_index = np.ascontiguousarray(sc.voxel_index, np.uint32)
+        self.aabb = np.ascontiguousarray(sc.aabb, np.float32).reshape(6)
+        self.side = int(sc.side)
+        self.triangles = np.ascontiguousarray(sc.triangles)
+        v = np.asarray(sc.vertices, np.float32)
+        self.vertices = np.zeros((v.shape[0], 4), np.float32)
+        self.vertices[:, :v.shape[1]] = v
+        self.surfaces = np.ascontiguousarray(sc.surfaces)
+        assert self.triangles.dtype.itemsize == 16 and self.surfaces.dtype.itemsize == 64
+
+    def closest_hit(self, pos, dirs, brute=False):
+        rays = np.ascontiguousarray(np.concatenate([pos, dirs], 1), np.float32)
+        n = rays.shape[0]
+        tri = np.zeros(n, np.uint32)
+        t = np.zeros(n, np.float32)
+        lib().refk_closest_hit(_p(rays), n, int(brute), _p(self.voxel_index), _p(self.aabb), self.side,
+                               _p(self.triangles), self.triangles.size, _p(self.vertices), _p(tri), _p(t))
+        return tri, t
+
+    def trace_steps(self, dirs, source, receiver, depth, rng_for_step, receiver_radius=0.1, initial_energy=1.0):
+        """raytracer::run's inner loop for one segment (raytracer.h:223-240) with the
+        stochastic finder (stochastic/finder.h:48-79): yields, per step, the reflection
+        records and the two impulse arrays exactly as the kernels wrote them.
+        rng_for_step(step) -> float32 [n, 2] (z, theta): the reference draws these on the host
+        (reflector.cpp:13-25); the caller supplies the stream."""
+        L = lib()
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        rays = np.zeros(n, RAY_DT)
+        rays["position"][:, :3] = np.asarray(source, np.float32)
+        rays["direction"][:, :3] = d
+        rcv = np.asarray(receiver, np.float32)
+        src = np.asarray(source, np.float32)
+        refl = np.zeros(n, REFL_DT)
+        L.refk_init_reflections(_p(refl), n)                                   # reflector.h:44-52
+        path = np.zeros(n, np.dtype([("volume", "<f4", (8,)), ("position", "<f4", (4,)), ("distance", "<f4"),
+                                     ("pad", "<f4", (3,))]))
+        L.refk_init_stochastic_path_info(_p(path), float(initial_energy), _p(src), n)   # finder.cpp:24-34
+        for step in range(depth):
+            rng = np.ascontiguousarray(rng_for_step(step), np.float32).reshape(n, 2)
+            L.refk_reflections(_p(rays), _p(rcv), _p(self.voxel_index), _p(self.aabb), self.side,
+                               _p(self.triangles), _p(self.vertices), _p(self.surfaces), _p(rng), _p(refl), n)
+            sto = np.zeros(n, IMPULSE_DT)
+            hit = np.zeros(n, IMPULSE_DT)
+            L.refk_stochastic(_p(refl), _p(rcv), float(receiver_radius), _p(self.triangles), _p(self.vertices),
+                              _p(self.surfaces), _p(path), _p(sto), _p(hit), n)
+            yield step, refl.copy(), sto, hit
+
+
+def histogram_from_steps(steps, n_bins, speed_of_sound=340.0, histogram_rate=1000.0, specular_from_step=0):
+    """stochastic_group_processor::process + energy_histogram_sum
+    (reflection_processor/stochastic_histogram.h:17-32,70-111): impulses with distance == 0 are
+    dropped (stochastic/finder.h:65-76); bin = size_t(time * sample_rate); specular (intersected)
+    output only when step >= max_image_source_order."""
+    hist = np.zeros((n_bins, 8))
+    dropped = 0
+    for step, _refl, sto, hit in steps:
+        groups = [sto] + ([hit] if step >= specular_from_step else [])
+        for g in groups:
+            live = g[g["distance"] != 0]
+            time = live["distance"].astype(np.float64) / speed_of_sound
+            b = (time * histogram_rate).astype(np.int64)
+            ok = b < n_bins
+            dropped += int((~ok).sum())
+            np.add.at(hist, b[ok], live["volume"][ok].astype(np.float64))
+    return hist, dropped
+
+
+# ---- mesh setup ----------------------------------------------------------------------------------
+def classify_scene(sc, min_corner, dims, spacing):
+    """set_node_inside + set_node_boundary_type (mesh.cpp:73-101) -> condensed_node array with
+    boundary_type set (boundary_index still 0)."""
+    s = RayScene(sc)
+    mc = np.asarray(min_corner, np.float32)
+    d = np.asarray(dims, np.int32)
+    n = int(d[0]) * int(d[1]) * int(d[2])
+    nodes = np.zeros(n, NODE_DT)
+    lib().refk_set_node_inside(_p(nodes), _p(mc), _p(d), float(spacing), _p(s.voxel_index), _p(s.aabb), s.side,
+                               _p(s.triangles), _p(s.vertices), n)
+    lib().refk_set_node_boundary_type(_p(nodes), _p(mc), _p(d), float(spacing), n)
+    return nodes
+
+
+def boundary_type_only(nodes, dims):
+    """set_node_boundary_type alone on nodes whose inside flags are already set."""
+    out = np.ascontiguousarray(nodes, NODE_DT).copy()
+    mc = np.zeros(3, np.float32)
+    d = np.asarray(dims, np.int32)
+    lib().refk_set_node_boundary_type(_p(out), _p(mc), _p(d), 1.0, out.size)
+    return out
+
+
+def coefficient_indices(sc, nodes, min_corner, dims, spacing, n1, n2, n3):
+    """the three finder kernels (boundary_coefficient_finder.cpp:66-124) on numbered nodes."""
+    s = RayScene(sc)
+    mc = np.asarray(min_corner, np.float32)
+    d = np.asarray(dims, np.int32)
+    nd = np.ascontiguousarray(nodes, NODE_DT)
+    b1 = np.zeros((max(n1, 1), 1), np.uint32)
+    b2 = np.zeros((max(n2, 1), 2), np.uint32)
+    b3 = np.zeros((max(n3, 1), 3), np.uint32)
+    L = lib()
+    L.refk_boundary_coefficient_finder_1d(_p(nd), _p(mc), _p(d), float(spacing), _p(b1), _p(s.voxel_index),
+                                          _p(s.aabb), s.side, _p(s.triangles), s.triangles.size, _p(s.vertices),
+                                          nd.size, 1)
+    L.refk_boundary_coefficient_finder_2d(_p(nd), _p(mc), _p(d), float(spacing), _p(b2), _p(b1), nd.size)
+    L.refk_boundary_coefficient_finder_3d(_p(nd), _p(mc), _p(d), float(spacing), _p(b3), _p(b1), nd.size)
+    return b1[:n1], b2[:n2], b3[:n3]

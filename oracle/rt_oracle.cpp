@@ -623,6 +623,13 @@ void rto_closest_surface(const rto_scene* s, const float* points3, size_t n, uin
     }
 }
 
+// the (z, theta) pair ray `base + i` consumes at `step` (stream 0): what the reference's host
+// draws per step and uploads as `rng` (reflector.cpp:13-25,35). Exposed so that the reference's
+// own kernels (oracle/_ref) can be fed the identical stream.
+void rto_step_rng(uint64_t seed, uint64_t base, size_t n, uint32_t step, float* out2) {
+    for (size_t i = 0; i < n; ++i) direction_rng(seed, uint32_t(base + i), step, 0u, &out2[2 * i], &out2[2 * i + 1]);
+}
+
 void rto_sincos(const float* theta, size_t n, float* s, float* c) {
     for (size_t i = 0; i < n; ++i) sincos_fixed(theta[i], &s[i], &c[i]);
 }

@@ -50,6 +50,7 @@ def lib():
         L.rto_ray_energy.argtypes = [C.c_uint64, vp, vp, C.c_float]
         L.rto_directions.argtypes = [C.c_uint64, C.c_uint64, sz, vp]
         L.rto_sincos.argtypes = [vp, sz, vp, vp]
+        L.rto_step_rng.argtypes = [C.c_uint64, C.c_uint64, sz, C.c_uint32, vp]
         L.rto_lut_index.argtypes = [vp, sz, vp, vp]
         L.rto_nodes_inside.argtypes = [vp, vp, vp, C.c_float, vp]
         L.rto_closest_surface.argtypes = [vp, vp, sz, vp, vp]
@@ -187,6 +188,13 @@ def ray_energy(total_rays, source, receiver, radius):
 def directions(seed, n, base=0):
     out = np.zeros((n, 3), np.float32)
     lib().rto_directions(int(seed), int(base), n, _p(out))
+    return out
+
+
+def step_rng(seed, n, step, base=0):
+    """(z, theta) per ray for one reflection step -- the stream trace() consumes"""
+    out = np.zeros((n, 2), np.float32)
+    lib().rto_step_rng(int(seed), int(base), n, int(step), _p(out))
     return out
 
 
