@@ -269,7 +269,16 @@ typedef struct {
 /* What core::scene_buffers uploads (spatial_division/scene_buffers.h:14-38) from a
  * voxelised_scene_data: the flattened voxel index of voxel_collection.cpp:9-37
  * (index[x*side*side + y*side + z] = offset of a run [count, tri, tri, ...]),
- * the voxel grid's AABB and side, triangles, vertices and surfaces. */
+ * the voxel grid's AABB and side, triangles, vertices and surfaces.
+ *
+ * PRECONDITION (as for the reference): every voxel's run lists at least the triangles that
+ * overlap the voxel's box -- a conservative superset is fine, a missing triangle is not. The
+ * reference's octree assigns triangles with an exact box/triangle overlap test
+ * (voxel_collection.cpp:9-37 over octree.cpp), wvb_voxelise() below does the same. The receiver
+ * visibility ray stops walking at the receiver's distance (the reference walks to the grid's
+ * edge, voxel.cpp:227-258): with conservative lists a hit that matters (t <= distance) is found
+ * in a voxel entered before that distance, so the two agree; with a list that misses an
+ * overlapping triangle both walks are wrong, in different ways. */
 typedef struct {
     const uint32_t* voxel_index;
     uint64_t voxel_index_count;

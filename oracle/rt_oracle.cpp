@@ -35,9 +35,13 @@
 //   * sin/cos/normalize: OpenCL's cos/sin/normalize have implementation-defined
 //     rounding. We use a fixed Cody-Waite + polynomial sincos for theta in
 //     [-pi, pi] and normalize(v) = v * (1 / sqrt(dot(v, v))).
-// Parity pinning: the reference holds no golden ray data; the oracle is pinned by
-// its own CPU-twin tests restated in tests/test_rt_oracle_kats.py (brute-force ==
-// voxel traversal, analytic shoebox image sources, energy equivalence).
+// Parity pinning: PINNED to reference-run output. The reference's own `reflections` and
+// `stochastic` kernels with their geometry / voxel / brdf sources are compiled for the host into
+// oracle/_ref by oracle/ref_recipe/build.py; tests/test_ref_pin_rt.py feeds both sides the same
+// directions and random stream and asserts the reflection records of every step bit-identical
+// and the histograms equal to 1e-12. On top: the reference's CPU-twin tests restated in
+// tests/test_rt_oracle_kats.py (brute-force == voxel traversal, analytic shoebox image sources,
+// energy equivalence).
 
 #ifdef _OPENMP
 #include <omp.h>

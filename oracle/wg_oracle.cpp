@@ -26,10 +26,13 @@
 //   impedance / flat coefficients     src/waveguide/include/waveguide/fitted_boundary.h:20-75
 //   peak biquads, convolve            src/waveguide/src/filters.cpp:10-31, include/waveguide/filters.h:48-61
 //
-// Parity pinning: the reference ships no golden pressure traces; the oracle is
-// pinned against the reference's own known-answer tests (see
-// tests/test_oracle_kats.py) and against the nine checked-in coefficient sets
-// of bin/boundary_test/output.soft/coefficients.txt (tests/golden/).
+// Parity pinning: PINNED to reference-run output. oracle/_ref/lib_ref.so is the reference's own
+// OpenCL-C kernel source (program.cpp:11-531, cl/utils.cpp, cl/filters.cpp, the struct strings)
+// compiled for the host by oracle/ref_recipe/build.py; tests/test_ref_pin_wg.py steps it and this
+// file on the same meshes and asserts bit identity of pressures, filter memories and error flags
+// in both arithmetic modes, tests/test_ref_pin_mesh.py does the same for the mesh-setup kernels.
+// On top: the reference's own known-answer tests (tests/test_oracle_kats.py) and the nine
+// checked-in coefficient sets of bin/boundary_test/output.soft/coefficients.txt (tests/golden/).
 //
 // Two arithmetic modes:
 //   Real=float  : pressures float, filters double  == the reference's types

@@ -80,7 +80,14 @@ struct dev_buf {
         n = count;
         if (!count) return;
         WVB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
-        if (zero) WVB_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+        if (zero) {
+            // The handles work on cudaStreamNonBlocking streams, which do not order against the
+            // legacy default stream a plain cudaMemset runs on, and a device memset is
+            // asynchronous to the host: wait for it here so that whatever stream touches the
+            // buffer next finds it zeroed.
+            WVB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+            WVB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+        }
         if (tally) *tally += count * sizeof(T);
     }
     void upload(const T* src, size_t count, size_t* tally = nullptr) {

@@ -192,6 +192,12 @@ wvb_status wvb_is_trace(wvb_is* s, const wvb_rt_trace_params* p, const float* di
         const uint32_t to_tree = std::min(order, p->depth);  // steps beyond depth do not exist
         const uint32_t to_host = reflections ? p->keep_steps : 0u;
         const uint32_t keep = std::max(to_tree, to_host);
+        // validate before anything is enqueued: the trace accumulates into the scene's histogram,
+        // so a call that fails afterwards would leave this segment's rays counted
+        WVB_REQUIRE(s->pushed + (uint64_t)n * to_tree <= s->max_elements, WVB_ERR_UNSUPPORTED,
+                    "more path elements pushed (%llu) than wvb_is_desc.max_elements (%llu)",
+                    (unsigned long long)(s->pushed + (uint64_t)n * to_tree),
+                    (unsigned long long)s->max_elements);
         dev_buf<rt::ReflectionPod> d;
         if (n && keep) d.alloc((size_t)n * keep, false);
         wvb_rt_trace_enqueue(s->scene, p, directions, n, d.p, keep);

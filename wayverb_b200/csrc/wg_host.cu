@@ -472,7 +472,9 @@ long long local_offset(const wvb_wg* w, uint64_t node, int* owned) {
     const int y = int(r % dy);
     const long long z = (long long)(r / dy);
     if (owned) *owned = 0;
-    if (z >= w->dim[2]) return -1;
+    // a node outside the mesh is a caller error, not "owned by another slab"
+    WVB_REQUIRE(z < w->dim[2], WVB_ERR_INVALID, "node %llu is outside the %dx%dx%d mesh",
+                (unsigned long long)node, w->dim[0], w->dim[1], w->dim[2]);
     const long long lz = z - w->z_begin + 1;
     if (lz < 0 || lz > w->g.nzl + 1) return -1;
     if (owned) *owned = (lz >= 1 && lz <= w->g.nzl);
