@@ -358,6 +358,28 @@ float wvb_rt_ray_energy(uint64_t total_rays, const float source[3], const float 
  * voxel grid's diagonal */
 uint32_t wvb_rt_safe_bins(const wvb_rt* rt, uint32_t depth, double speed_of_sound, double rate);
 
+/* ---- scene preparation (host code, once per scene) ------------------------------ */
+/* make_voxelised_scene_data(scene, octree_depth, padding) + get_flattened
+ * (spatial_division/voxelised_scene_data.h:27-71, ndim_tree.h:47-117, voxel_collection.h:66-85,
+ * voxel_collection.cpp:9-37): the AABB of the vertices padded by `padding`, an octree of
+ * `octree_depth` levels over the triangle indices (a child keeps the triangles of its parent
+ * that overlap the child's box grown by 0.001, geo/box.cpp:21-27 over
+ * geo/tri_cube_intersection.cpp:131-170) and its leaves as side^3 voxels, side = 2^depth,
+ * flattened as wvb_rt_scene_desc.voxel_index wants them. The engine calls it with depth 5,
+ * padding 0.1 (combined/src/threaded_engine.cpp:123).
+ * Two-pass: index_out == NULL returns the length in *count. */
+wvb_status wvb_voxelise(const wvb_float3* vertices, uint32_t num_vertices, const wvb_triangle* triangles,
+                        uint32_t num_triangles, uint32_t octree_depth, float padding, float aabb_min[3],
+                        float aabb_max[3], uint32_t* index_out, uint64_t capacity, uint64_t* count);
+/* What scene_data_loader (core/src/scene_data_loader.cpp:17-70, assimp) yields for a Wavefront
+ * OBJ: vertices, triangles (polygons fan-triangulated) with a material index each, and the
+ * material names ('\n'-terminated, in index order; index = order of first `usemtl`).
+ * Two-pass: with vertices/triangles/material_names NULL the three counts are returned; then
+ * *num_vertices / *num_triangles / *material_names_length are the capacities on entry. */
+wvb_status wvb_obj_parse(const char* text, uint64_t length, wvb_float3* vertices, uint64_t* num_vertices,
+                         wvb_triangle* triangles, uint64_t* num_triangles, char* material_names,
+                         uint64_t* material_names_length);
+
 /* ---- mesh construction (the step before waveguide::run) ---------------------- */
 
 typedef struct wvb_mesh wvb_mesh;

@@ -38,6 +38,37 @@ def available() -> bool:
     return recipe.build() is not None
 
 
+_native_wg = None
+
+
+def use_native_wg() -> bool:
+    """bench.py's reference arm: recompile the generated waveguide unit (oracle/_ref/ref_wg_f32.cpp,
+    the reference's kernel source behind the prelude -- it travels with oracle/_ref) with
+    -O3 -march=native ON this machine and let Sim(real="float") step through it. Same source, same
+    -ffp-contract=off. Returns False (portable lib_ref.so stays in use) if that is not possible."""
+    global _native_wg
+    if _native_wg is not None:
+        return bool(_native_wg)
+    import subprocess
+    src = os.path.join(recipe.OUT, "ref_wg_f32.cpp")
+    out_dir = os.path.join(recipe.OUT, "native")
+    out = os.path.join(out_dir, "lib_ref_wg_f32.so")
+    _native_wg = False
+    if os.path.exists(src):
+        try:
+            os.makedirs(out_dir, exist_ok=True)
+            flags = [f for f in recipe.FLAGS if f != "-O2"] + ["-O3", "-march=native"]
+            subprocess.run([recipe.CXX] + flags + ["-shared", "-o", out, src], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            L = C.CDLL(out)
+            L.refk_f32_wg_step.restype = C.c_int
+            L.refk_f32_wg_step.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_size_t]
+            _native_wg = L
+        except (subprocess.CalledProcessError, OSError):
+            _native_wg = False
+    return bool(_native_wg)
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -125,7 +156,7 @@ class Sim:
 
     def step(self, n=1) -> int:
         dx, dy, dz = self.mesh.dims
-        fn = getattr(lib(), "refk_" + self.p + "wg_step")
+        fn = getattr(_native_wg if (_native_wg and self.p == "f32_") else lib(), "refk_" + self.p + "wg_step")
         flags = 0
         for _ in range(int(n)):
             # waveguide.h:82-97 flag reset + kernel, :123 swap

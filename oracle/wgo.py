@@ -36,12 +36,35 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_native = False
+
+
+def use_native() -> bool:
+    """bench.py's CPU legs: load the -O3 -march=native build of the same source (Makefile target
+    `native`, compiled ON the machine that runs it -- a -march=native binary must never travel).
+    Must be called before the first lib(); falls back to the portable build when g++ fails."""
+    global _LIB_PATH, _native
+    if _lib is not None:
+        return _native
+    path = os.path.join(_HERE, "_build", "native", "libwgoracle.so")
+    try:
+        subprocess.run(["make", "-B", "-C", _HERE, "_build/native/libwgoracle.so"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _LIB_PATH, _native = path, True
+    except (subprocess.CalledProcessError, OSError):
+        _native = False
+    return _native
+
+
+def is_native() -> bool:
+    return _native
 
 
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if not _native:
+            build()
         L = C.CDLL(_LIB_PATH)
         vp, sz, u32p, dp = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_double)
         L.wgo_create.restype = vp

@@ -32,9 +32,14 @@ def test_smallest_boxes_and_zero_length_runs(dims):
         sim = wgo.Sim(om)
         sim.run(src, np.array([1.0, 0.0, 0.0, 0.0, 0.0]), [src])
         assert np.array_equal(g.field(), sim.field())
-        # nodes this handle does not hold are ignored on write and read back as not owned
-        g.write(om.num_nodes + 10, 3.0)
-        assert not g.owns(om.num_nodes + 10)
+        # a node index outside the mesh is a caller error (not "owned by another slab"): the
+        # call fails with WVB_ERR_INVALID and the field is untouched
+        for bad_call in (lambda: g.write(om.num_nodes + 10, 3.0), lambda: g.read(om.num_nodes + 10),
+                         lambda: g.run_device(om.num_nodes, np.ones(2), [src]),
+                         lambda: g.run_device(src, np.ones(2), [om.num_nodes + 3])):
+            with pytest.raises(_lib.WvbError) as e:
+                bad_call()
+            assert "outside" in str(e.value)
         assert np.array_equal(g.field(), sim.field())
 
 

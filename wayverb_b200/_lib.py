@@ -121,6 +121,8 @@ RT_SYMBOLS = [
     "wvb_rt_directions", "wvb_rt_comm_init", "wvb_rt_allreduce_histogram",
 ]
 
+SCENE_SYMBOLS = ["wvb_voxelise", "wvb_obj_parse"]
+
 _lib = None
 
 
@@ -202,6 +204,9 @@ def lib():
     L.wvb_is_trace.argtypes = [vp, C.POINTER(RtTraceParams), vp, u64, u32, vp, C.POINTER(u64),
                                C.POINTER(C.c_float)]
     L.wvb_is_results.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64 * 4), C.POINTER(C.c_float)]
+    L.wvb_voxelise.argtypes = [vp, u32, vp, u32, u32, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
+                               vp, u64, C.POINTER(u64)]
+    L.wvb_obj_parse.argtypes = [C.c_char_p, u64, vp, C.POINTER(u64), vp, C.POINTER(u64), vp, C.POINTER(u64)]
     _lib = L
     return L
 

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("WVB_LIB_OUT") or os.path.join(HERE, "libwvb200.so")
-SOURCES = ["wg_host.cu", "rt_host.cu", "mesh_host.cu", "is_host.cu", "lrs_design.cpp"]
+SOURCES = ["wg_host.cu", "rt_host.cu", "mesh_host.cu", "is_host.cu", "lrs_design.cpp", "scene_host.cpp"]
 HEADERS = ["common.h", "nccl_dyn.h", "wg_kernels.cuh", "rt_kernels.cuh", "mesh_kernels.cuh", "is_kernels.cuh",
            os.path.join("..", "..", "include", "wvb200.h")]
 
@@ -56,6 +56,26 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PROBE = os.path.join(HERE, "libwvb200_probe.so")
+
+
+def build_probe(force: bool = False) -> str:
+    """bench.py's end-to-end leg through the C++ `waveguide::run` template (csrc/e2e_probe.cpp):
+    host-only C++14, linked against libwvb200.so (found next to it at run time)."""
+    src = os.path.join(CSRC, "e2e_probe.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "wayverb_b200", "waveguide.hpp"), LIB]
+    if not force and os.path.exists(PROBE) and all(os.path.getmtime(d) <= os.path.getmtime(PROBE) for d in deps):
+        return PROBE
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-std=c++14", "-O2", "-fPIC", "-shared", "-o", PROBE, src, "-L" + HERE, "-l:libwvb200.so",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return PROBE
+
+
 if __name__ == "__main__":
     import sys
     print(build_lib(force=True, verbose="-v" in sys.argv))
+    print(build_probe(force=True))
