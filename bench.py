@@ -297,6 +297,9 @@ class Ctx:
         return box[0]
 
 
+HALO_FLAGS = 0  # set from --halo
+
+
 def slab_handle(ctx, gdims, coeffs, kernel=None):
     """this rank's z-slab of the cuboid mesh `gdims` (balanced contiguous planes)"""
     import wayverb_b200 as wvb
@@ -305,7 +308,8 @@ def slab_handle(ctx, gdims, coeffs, kernel=None):
     lo, hi = max(z0 - 1, 0), min(z1 + 1, gdims[2])
     mesh = wvb.cuboid_mesh(gdims, [coeffs], z0=lo, nz=hi - lo)
     wg = wvb.Waveguide(mesh, device=ctx.local, z_range=(z0, z1), rank=ctx.rank, nranks=ctx.world,
-                       nccl_unique_id=ctx.fresh_uid(), kernel=_lib.KERNEL_AUTO if kernel is None else kernel)
+                       nccl_unique_id=ctx.fresh_uid(), kernel=_lib.KERNEL_AUTO if kernel is None else kernel,
+                       flags=HALO_FLAGS)
     return mesh, wg, (z0, z1)
 
 
@@ -376,7 +380,7 @@ def time_mesh(ctx, gdims, coeffs, steps, warmup, sampler=None):
     nodes = gdims[0] * gdims[1] * gdims[2]
     return {"value": nodes / ms / 1e3, "unit": "Mnode-updates/s", "ms_per_step": ms,
             "mesh": "%dx%dx%d" % gdims, "planes_per_gpu": z1 - z0, "steps": steps,
-            "kernel": info["kernel_variant"], "tile": list(info["tile"])}
+            "kernel": info["kernel_variant"], "tile": list(info["tile"]), "halo": info["halo"]}
 
 
 def probe_lib():
@@ -407,6 +411,8 @@ def ray_row(ctx, sampler, with_cpu):
         if ctx.world > 1:
             g.comm_init(ctx.fresh_uid(), ctx.rank, ctx.world)
         g.trace(None, src, rcv, depth, n_rays=1 << 14, total_rays=total, seed=1)      # warm-up
+        if ctx.world > 1:
+            g.allreduce_histogram()   # the communicator's first collective sets up its connections
         g.reset_histogram()
         ctx.barrier()
         t0 = time.perf_counter()
@@ -467,6 +473,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", default="512,512,512", help="per-GPU slab (x,y,z planes per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "p2p", "p2p+overlap", "nccl+overlap"],
+                    help="ghost-plane transport (auto: peer-to-peer stores when mappable, else NCCL)")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline only: skip config4 / strong / slab256 / ray rows")
     args = ap.parse_args()
@@ -482,6 +490,9 @@ def main():
     from wayverb_b200 import _lib
     rank, world = ctx.rank, ctx.world
     coeffs = plaster_coeffs(_lib.COEFF_DT)
+    global HALO_FLAGS
+    HALO_FLAGS = {"auto": _lib.HALO_AUTO, "nccl": _lib.HALO_NCCL, "p2p": _lib.HALO_P2P}[args.halo.split("+")[0]] | \
+        (_lib.HALO_OVERLAP if args.halo.endswith("+overlap") else 0)
 
     parity = multi_gpu_parity(ctx, coeffs) if world > 1 else None
     if parity is not None and not parity["identical"]:
@@ -620,7 +631,8 @@ def main():
             "config": {
                 "workload": "%dx%dx%d cuboid mesh (%dx%dx%d z-slab per GPU), plaster 6th-order LRS walls "
                             "(BASELINE config 3 at N=1), centred impulse" % (gdims + (sx, sy, sz)),
-                "parallelism": "z-slabs x%d, one ghost-plane exchange per face per step" % world,
+                "parallelism": "z-slabs x%d, one ghost-plane exchange per face per step (transport: %s)"
+                               % (world, info0["halo"]),
                 "l2": "no flush needed: the two fp64 pressure arrays are %.2f GB per GPU, far larger than "
                       "the 126 MB L2" % (2 * nodes_local * 8 / 1e9),
                 "kernel": info0["kernel_variant"], "tile": list(info0["tile"]),

@@ -715,6 +715,67 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
 }
 
 
+// ---- the reference's own parameter types (raytracer.h:188-201) --------------------------------
+/// `flatten` is the customisation point between a caller's scene type and the arrays the device
+/// walks. This generic version works for anything with the interface of the reference's
+/// `core::voxelised_scene_data<cl_float3, surface<8>>` (voxelised_scene_data.h:45-46):
+///   get_voxels()      -> voxel_collection<3>: get_aabb().get_min()/get_max() (.x .y .z),
+///                        get_side(), get_voxel(index3{x, y, z}) -> range of triangle indices
+///   get_scene_data()  -> get_triangles(), get_vertices(), get_surfaces()
+/// and restates get_flattened (voxel_collection.cpp:9-37) + make_scene_buffers
+/// (scene_buffers.h:14-38). A caller whose type differs provides its own
+/// `flatten(const T&) -> core::flattened_scene` next to T (found by ADL).
+template <typename Voxelised>
+auto flatten(const Voxelised& voxelised)
+        -> decltype(voxelised.get_voxels().get_side(), voxelised.get_scene_data().get_triangles(),
+                    core::flattened_scene{}) {
+    core::flattened_scene out;
+    const auto& voxels = voxelised.get_voxels();
+    const auto side = size_t(voxels.get_side());
+    const auto aabb = voxels.get_aabb();
+    out.aabb_min = core::vec3{float(aabb.get_min().x), float(aabb.get_min().y), float(aabb.get_min().z)};
+    out.aabb_max = core::vec3{float(aabb.get_max().x), float(aabb.get_max().y), float(aabb.get_max().z)};
+    out.side = cl_uint(side);
+    out.voxel_index.assign(side * side * side, 0);
+    using index3 = std::decay_t<decltype(voxelised.voxel_index_type())>;
+    for (size_t x = 0; x != side; ++x) {
+        for (size_t y = 0; y != side; ++y) {
+            for (size_t z = 0; z != side; ++z) {
+                out.voxel_index[x * side * side + y * side + z] = cl_uint(out.voxel_index.size());
+                const auto& v = voxels.get_voxel(index3(x, y, z));
+                out.voxel_index.emplace_back(cl_uint(v.size()));
+                for (const auto& i : v) out.voxel_index.emplace_back(cl_uint(i));
+            }
+        }
+    }
+    const auto& scene = voxelised.get_scene_data();
+    for (const auto& t : scene.get_triangles()) out.triangles.push_back(core::triangle{t.surface, t.v0, t.v1, t.v2});
+    for (const auto& v : scene.get_vertices()) out.vertices.push_back(cl_float3{{v.s[0], v.s[1], v.s[2], 0.0f}});
+    for (const auto& sf : scene.get_surfaces()) {
+        core::surface<core::simulation_bands> o{};
+        for (int b = 0; b < core::simulation_bands; ++b) {
+            o.absorption.s[b] = sf.absorption.s[b];
+            o.scattering.s[b] = sf.scattering.s[b];
+        }
+        out.surfaces.push_back(o);
+    }
+    return out;
+}
+
+/// raytracer::run with the reference's parameter list: the scene is any type `flatten` accepts
+/// (the reference's voxelised_scene_data among them), source and receiver any vector with
+/// .x .y .z (glm::vec3). The processors' get_processor still receives the flattened scene.
+template <typename It, typename Scene, typename Vec3, typename PerStepCallback, typename... Callbacks,
+          typename = std::enable_if_t<!std::is_same<std::decay_t<Scene>, core::flattened_scene>::value>>
+auto run(It b_direction, It e_direction, const core::compute_context& cc, const Scene& voxelised,
+         const Vec3& source, const Vec3& receiver, const core::environment& environment,
+         const std::atomic_bool& keep_going, PerStepCallback&& per_step_callback,
+         std::tuple<Callbacks...> callbacks, uint64_t seed = std::random_device{}()) {
+    return run(b_direction, e_direction, cc, flatten(voxelised), core::vec3{float(source.x), float(source.y), float(source.z)},
+               core::vec3{float(receiver.x), float(receiver.y), float(receiver.z)}, environment, keep_going,
+               std::forward<PerStepCallback>(per_step_callback), std::move(callbacks), seed);
+}
+
 /// image_source/run.h:12-47: raytracer::run with only the image-source processor, every
 /// reflection step eligible (max order = the reflection depth).
 namespace image_source {

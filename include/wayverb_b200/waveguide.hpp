@@ -30,117 +30,9 @@
 
 #include "../wvb200.h"
 #include "cl_compat.hpp"
-
-namespace util {
-namespace aligned {
-template <typename T>
-using vector = std::vector<T>;  // utilities/aligned/vector.h: std::vector with an aligned allocator
-}  // namespace aligned
-}  // namespace util
+#include "core.hpp"
 
 namespace wayverb {
-namespace core {
-
-enum class device_type { cpu, gpu };
-
-/// cl::Context + cl::Device in the reference (cl/common.h:13-22); here a CUDA
-/// device ordinal. There is no CPU device: device_type::cpu is refused.
-class compute_context final {
-public:
-    compute_context() = default;
-    explicit compute_context(int cuda_device) : device{cuda_device} {}
-    explicit compute_context(device_type type) {
-        if (type != device_type::gpu) {
-            throw std::runtime_error{"wayverb_b200 has no CPU path: a B200 is required."};
-        }
-    }
-    int device{0};
-};
-
-namespace exceptions {
-struct value_is_nan final : public std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
-struct value_is_inf final : public std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
-}  // namespace exceptions
-
-/// core/environment.h:6-13
-struct environment final {
-    double speed_of_sound{340.0};
-    double acoustic_impedance{400.0};
-};
-constexpr double get_ambient_density(const environment& s) { return s.acoustic_impedance / s.speed_of_sound; }
-/// stands in for glm::vec3 in signatures
-struct vec3 final {
-    float x, y, z;
-};
-
-namespace detail {
-inline void check(wvb_status s) {
-    if (s != WVB_OK && s != WVB_ERR_SIM) {
-        throw std::runtime_error{std::string{"libwvb200: "} + wvb_last_error()};
-    }
-}
-}  // namespace detail
-
-template <typename T>
-size_t items_in_buffer(const cl::Buffer& buffer) {
-    return buffer.items();
-}
-
-template <typename T>
-T read_value(cl::CommandQueue&, const cl::Buffer& buffer, size_t index) {
-    double v = 0;
-    detail::check(wvb_wg_read_f64(buffer.handle(), index, &v, nullptr));
-    return static_cast<T>(v);
-}
-
-template <typename T>
-void write_value(cl::CommandQueue&, cl::Buffer& buffer, size_t index, T val) {
-    detail::check(wvb_wg_write_f64(buffer.handle(), index, static_cast<double>(val)));
-}
-
-template <typename T>
-util::aligned::vector<T> read_from_buffer(cl::CommandQueue&, const cl::Buffer& buffer);
-
-template <>
-inline util::aligned::vector<double> read_from_buffer<double>(cl::CommandQueue&,
-                                                              const cl::Buffer& buffer) {
-    util::aligned::vector<double> ret(buffer.items());
-    detail::check(wvb_wg_read_field(buffer.handle(), ret.data()));
-    return ret;
-}
-template <>
-inline util::aligned::vector<float> read_from_buffer<float>(cl::CommandQueue&,
-                                                            const cl::Buffer& buffer) {
-    util::aligned::vector<float> ret(buffer.items());
-    detail::check(wvb_wg_read_field_f32(buffer.handle(), ret.data()));
-    return ret;
-}
-
-/// callback_accumulator (core/callback_accumulator.h): collects what a
-/// postprocessor returns each step.
-template <typename Callback>
-class callback_accumulator final {
-public:
-    template <typename... Ts>
-    explicit callback_accumulator(Ts&&... ts) : callback_{std::forward<Ts>(ts)...} {}
-    template <typename... Ts>
-    void operator()(Ts&&... ts) {
-        output_.emplace_back(callback_(std::forward<Ts>(ts)...));
-    }
-    const auto& get_output() const { return output_; }
-    const Callback& get_callback() const { return callback_; }
-
-private:
-    Callback callback_;
-    util::aligned::vector<typename Callback::return_type> output_;
-};
-
-}  // namespace core
-
 namespace waveguide {
 
 // ---- PODs: the layouts are the contract (see include/wvb200.h for file:line) ----
@@ -474,6 +366,19 @@ inline size_t run_stock(const core::compute_context& cc, const mesh& mesh, size_
 }
 
 // ---- stock processors (same behaviour as the reference's) ---------------------------------
+#ifdef WVB_WITH_REFERENCE_HEADERS
+}  // namespace waveguide
+}  // namespace wayverb
+// Overlay mode: the stock processors are the reference's OWN headers, compiled unmodified
+// against include/compat (core/cl/common.h -> core.hpp). Needs the reference's
+// src/waveguide/include on the include path, after include/compat.
+#include "waveguide/postprocessor/node.h"
+#include "waveguide/preprocessor/hard_source.h"
+#include "waveguide/preprocessor/soft_source.h"
+namespace wayverb {
+namespace waveguide {
+namespace preprocessor {
+#else
 namespace preprocessor {
 /// hard_source.h:9-37: overwrite the node with the next sample every step.
 template <typename It>
@@ -514,6 +419,7 @@ template <typename It>
 auto make_soft_source(size_t node, It begin, It end) {
     return soft_source<It>{node, begin, end};
 }
+#endif  // WVB_WITH_REFERENCE_HEADERS
 /// gaussian.cpp:10-53: at step 0 the whole field is set to a 3-d gaussian centred
 /// on `centre_pos` (evaluated on the host in the reference's mixed float/double
 /// arithmetic, written as float values); the run lasts `steps` steps.
@@ -568,6 +474,7 @@ inline std::array<cl_uint, 6> compute_neighbors(const mesh_descriptor& d, size_t
 }
 
 namespace postprocessor {
+#ifndef WVB_WITH_REFERENCE_HEADERS
 /// node.cpp:14-18: the pressure at one node each step.
 class node final {
 public:
@@ -581,6 +488,7 @@ public:
 private:
     size_t output_node_;
 };
+#endif  // WVB_WITH_REFERENCE_HEADERS (else: the reference's postprocessor/node.h + node.cpp)
 /// directional_receiver.cpp:10-69: pressure + intensity (velocity from the pressure
 /// gradient of the six neighbours, integrated in double on the host). Reads are
 /// `cl_float` like the reference's, i.e. the fp64 device values are converted.

@@ -99,6 +99,17 @@ enum {
     WVB_WG_KERNEL_DIRECT = 1, /* register z-march, plain coalesced loads (bring-up / cross-check) */
     WVB_WG_KERNEL_TMA = 2     /* TMA-staged shared-memory plane ring (the production kernel)       */
 };
+/* wvb_wg_desc.flags, bits 8-15: TMA tile rows (0 = default), bits 16-27: z chunks (0 = auto) */
+/* ghost-plane transport between z-neighbours (wvb_wg_desc.flags, bits 28-29) */
+enum {
+    WVB_WG_HALO_AUTO = 0u << 28, /* peer-to-peer stores when the neighbours' memory can be mapped, else NCCL */
+    WVB_WG_HALO_NCCL = 1u << 28, /* one grouped ncclSend/ncclRecv per step                                   */
+    WVB_WG_HALO_P2P = 2u << 28   /* face planes stored straight into the neighbours' ghost planes over
+                                    NVLink (CUDA IPC mappings), release/acquire flags; create fails if the
+                                    mapping is impossible                                                  */
+};
+/* bit 30: update the two face planes first and exchange them underneath the interior update */
+#define WVB_WG_HALO_OVERLAP (1u << 30)
 
 /* What waveguide::run receives through `mesh` (mesh.h:12-26, setup.h:27-85),
  * restricted to the z-slab this handle owns. */
@@ -226,7 +237,7 @@ typedef struct {
     int32_t kernel_variant;     /* WVB_WG_KERNEL_* actually in use              */
     int32_t tile[3];            /* x, y tile and z chunk of the stencil kernel  */
     int32_t sm_count;
-    int32_t pad_;
+    int32_t halo;               /* ghost-plane transport: 0 none (one rank), 1 NCCL, 2 peer-to-peer; +4 = overlapped */
 } wvb_wg_info;
 wvb_status wvb_wg_get_info(wvb_wg* wg, wvb_wg_info* info);
 

@@ -68,7 +68,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for dims, kernel in (((140, 40, 12 * world + 5), _lib.KERNEL_TMA), ((37, 29, 8 * world + 3), _lib.KERNEL_DIRECT)):
+    cases = [((140, 40, 12 * world + 5), _lib.KERNEL_TMA, _lib.HALO_AUTO),
+             ((140, 40, 12 * world + 5), _lib.KERNEL_TMA, _lib.HALO_NCCL),
+             ((140, 40, 12 * world + 5), _lib.KERNEL_TMA, _lib.HALO_P2P | _lib.HALO_OVERLAP),
+             ((37, 29, 8 * world + 3), _lib.KERNEL_DIRECT, _lib.HALO_P2P),
+             ((37, 29, 8 * world + 3), _lib.KERNEL_DIRECT, _lib.HALO_NCCL | _lib.HALO_OVERLAP)]
+    for dims, kernel, halo in cases:
         # an ncclUniqueId serves exactly one communicator: a fresh one per handle
         box = [wvb.waveguide.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -85,11 +90,14 @@ def main():
         src = mesh.index(dx // 2, dy // 2, b0 - 1)
         rcv = [mesh.index(5, 6, 3), mesh.index(dx - 6, dy - 5, dz - 4), src]
         with wvb.Waveguide(mesh, device=local, z_range=(z0, z1), rank=rank, nranks=world,
-                           nccl_unique_id=uid, kernel=kernel) as g:
+                           nccl_unique_id=uid, kernel=kernel, flags=halo) as g:
             done, out, flag = g.run_device(src, sig, rcv, soft=True, check_interval=7)
+            # a second run on the same handle: plain steps (the captured per-step graph where
+            # the transport allows one) continuing from the state the first run left
+            flag2 = g.step(9)
             field = g.field()
             info = g.info()
-        assert done == steps and flag == 0, (done, flag)
+        assert done == steps and flag == 0 and flag2 == 0, (done, flag, flag2)
         out_t = torch.from_numpy(out).cuda()
         dist.all_reduce(out_t)  # receivers not owned by a rank are written as 0
         parts = [None] * world
@@ -98,13 +106,14 @@ def main():
             om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [plaster()])
             sim = wgo.Sim(om)
             _, want_out, wflag = sim.run(src, sig, rcv, soft=True)
+            wflag |= sim.step(9)
             want = sim.field()
             got = np.concatenate(parts)
             same_f = np.array_equal(got, want)
             same_o = np.array_equal(out_t.cpu().numpy(), want_out)
             rms = np.sqrt(np.mean((got - want) ** 2)) / np.abs(want).max()
-            print("dims %s kernel %s ranks %d: field identical=%s (rel RMS %.1e), traces identical=%s"
-                  % (dims, info["kernel_variant"], world, same_f, rms, same_o), flush=True)
+            print("dims %s kernel %s halo %s ranks %d: field identical=%s (rel RMS %.1e), traces identical=%s"
+                  % (dims, info["kernel_variant"], info["halo"], world, same_f, rms, same_o), flush=True)
             ok = ok and same_f and same_o and wflag == 0
     ok = ray_check(rank, world, local) and ok
     res = torch.tensor([1 if ok else 0], device="cuda")

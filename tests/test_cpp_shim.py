@@ -175,3 +175,89 @@ def test_raytracer_run_template(tmp_path):
         elems[:, b:e] = rto.path_elements(refl, 4)
     want, _ = rto.image_source(o, elems, src, rcv)
     assert got.shape == want.shape and np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+# ---- the shim as an overlay on the reference tree ---------------------------------------------
+REFERENCE = "/root/reference/src"
+OVERLAY_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "test_overlay")
+
+
+def build_overlay():
+    """tests/cpp/test_overlay.cpp + the reference's UNMODIFIED hard_source.h / soft_source.h /
+    postprocessor/node.h / node.cpp, compiled against include/compat. Needs /root/reference,
+    so it is built here (build container) and the executable travels to the GPU box
+    (tests/cpp/_build is git-ignored, not gpurun-ignored)."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_overlay.cpp")
+    os.makedirs(os.path.dirname(OVERLAY_EXE), exist_ok=True)
+    cmd = [GXX, "-std=c++14", "-O1", "-Wall", "-DWVB_WITH_REFERENCE_HEADERS",
+           "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(REFERENCE, "waveguide", "include"), "-I", os.path.join(REFERENCE, "utilities", "include"),
+           src, os.path.join(REFERENCE, "waveguide", "src", "postprocessor", "node.cpp"),
+           "-L", os.path.join(ROOT, "wayverb_b200"), "-l:libwvb200.so", "-Wl,-rpath," + os.path.join(ROOT, "wayverb_b200"),
+           "-Wl,-rpath,$ORIGIN/../../../wayverb_b200", "-o", OVERLAY_EXE]
+    subprocess.run(cmd, check=True)
+    return OVERLAY_EXE
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="/root/reference is only present in the build container")
+def test_overlay_compiles_against_unmodified_reference_headers():
+    """the reference's own processor headers + node.cpp compile and link against
+    include/compat + libwvb200.so; the shim's re-declarations are switched off
+    (WVB_WITH_REFERENCE_HEADERS), so there is no ODR clash"""
+    from wayverb_b200 import build as b
+    b.build_lib()
+    exe = build_overlay()
+    assert os.path.exists(exe)
+    # and without the macro the same translation unit must NOT compile: the static_assert
+    # that node::return_type is float (the reference's) guards against silently testing the shim's copy
+    r = subprocess.run([GXX, "-std=c++14", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "test_overlay.cpp")], capture_output=True, text=True)
+    assert r.returncode != 0 and "not the reference's" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("soft", [False, True])
+def test_overlay_reference_processors_drive_waveguide_run(soft):
+    if os.path.isdir(REFERENCE):
+        build_overlay()
+    if not os.path.exists(OVERLAY_EXE):
+        pytest.skip("tests/cpp/_build/test_overlay was not built (needs /root/reference at build time)")
+    steps, c = 60, wgo.to_flat(0.2)
+    r = subprocess.run([OVERLAY_EXE, str(steps), "%.17g" % c["b"][0]] + (["soft"] if soft else []),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr)
+    lines = r.stdout.strip().splitlines()
+    meta = lines[0].split()
+    src, rcv = int(meta[2]), int(meta[4])
+    got = np.array([float(v) for v in lines[1:]], np.float32)
+    dims = (30, 24, 20)
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [c])
+    assert src == om.index(14, 11, 9) and rcv == om.index(19, 13, 8)
+    sig = np.zeros(steps, np.float32)
+    sig[0] = 1.0
+    if soft:
+        sig[2] = -0.5
+    # what the reference's headers do, step by step, on the oracle: hard_source writes the sample;
+    # soft_source reads the node AS cl_float (soft_source.h:21-22), adds, writes; node reads cl_float
+    sim = wgo.Sim(om)
+    want = []
+    for s in range(steps):
+        if soft:
+            sim.write(src, float(np.float32(sim.read(src))) + float(sig[s]))
+        else:
+            sim.write(src, float(sig[s]))
+        want.append(np.float32(sim.read(rcv)))
+        assert sim.step(1) == 0
+    assert np.abs(got).max() > 0
+    assert np.array_equal(got, np.array(want, np.float32))
+
+
+@pytest.mark.gpu
+def test_overlay_raytracer_run_with_reference_parameter_types():
+    if os.path.isdir(REFERENCE):
+        build_overlay()
+    if not os.path.exists(OVERLAY_EXE):
+        pytest.skip("tests/cpp/_build/test_overlay was not built (needs /root/reference at build time)")
+    r = subprocess.run([OVERLAY_EXE, "rt"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr)
+    assert "OVERLAY_RT_OK" in r.stdout

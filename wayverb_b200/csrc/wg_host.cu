@@ -57,9 +57,17 @@ encode_tiled_fn get_encode_tiled() {
     return fn;
 }
 
+// Tuning knobs read from the environment exist only in builds made with -DWVB_DEBUG_KNOBS
+// (tools/sweep_wg.py, tools/ab_lib.py build such a library): the shipped library's kernel
+// choice depends on the descriptor alone.
 int env_int(const char* name, int dflt) {
+#ifdef WVB_DEBUG_KNOBS
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 struct blist_host {
@@ -111,6 +119,17 @@ struct wvb_wg {
     int fast_div = 1, pf = 4, minb = 1;
     int sm_count = 0;
     nccl::comm_t comm = nullptr;
+    // ghost-plane exchange over peer-mapped memory (see wg_halo_push in wg_kernels.cuh)
+    enum { HALO_NONE = 0, HALO_NCCL = 1, HALO_P2P = 2 };
+    int halo = HALO_NONE;
+    struct peer_t {
+        double* P[2] = {nullptr, nullptr};         // the neighbour's pressure arrays, mapped here
+        unsigned long long* flags = nullptr;       // the neighbour's flag words, mapped here
+        int nzl = 0;
+    } below, above;
+    dev_buf<unsigned long long> halo_flags;    // [0] written by the rank below, [1] by the rank above
+    dev_buf<unsigned long long> halo_counter;  // exchanges done
+    dev_buf<unsigned int> halo_ticket;
     size_t device_bytes = 0;
     uint64_t launches = 0;
     uint64_t air_nodes = 0;
@@ -118,6 +137,12 @@ struct wvb_wg {
 
     ~wvb_wg() {
         cudaSetDevice(dev);
+        cudaDeviceSynchronize();
+        for (peer_t* p : {&below, &above}) {
+            for (void* q : {(void*)p->P[0], (void*)p->P[1], (void*)p->flags}) {
+                if (q) cudaIpcCloseMemHandle(q);
+            }
+        }
         if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -372,8 +397,28 @@ void nccl_check(int r, const char* what) {
 // one ghost-plane exchange of array `a` (both faces) with the z-neighbours
 void exchange_ghosts(wvb_wg* w, double* a, cudaStream_t st) {
     if (w->nranks <= 1) return;
-    auto& n = nccl::get();
     const size_t cnt = (size_t)w->g.plane;
+    if (w->halo == wvb_wg::HALO_P2P) {
+        const int which = a == w->P[0].p ? 0 : 1;
+        const bool lo = w->rank > 0, hi = w->rank < w->nranks - 1;
+        // my plane 1 -> the top ghost plane (nzl + 1) of the rank below; my plane nzl -> plane 0
+        // of the rank above
+        const float4* src_lo = reinterpret_cast<const float4*>(a + cnt);
+        const float4* src_hi = reinterpret_cast<const float4*>(a + cnt * w->g.nzl);
+        float4* dst_lo = lo ? reinterpret_cast<float4*>(w->below.P[which] + cnt * (w->below.nzl + 1)) : nullptr;
+        float4* dst_hi = hi ? reinterpret_cast<float4*>(w->above.P[which]) : nullptr;
+        const uint32_t n16 = (uint32_t)(cnt / 2);
+        const int blocks = std::max(1, std::min(w->sm_count, (int)((n16 + 1023) / 1024)));
+        wg_halo_push<<<blocks, 256, 0, st>>>(src_lo, dst_lo, src_hi, dst_hi, n16,
+                                             lo ? w->below.flags + 1 : nullptr,
+                                             hi ? w->above.flags + 0 : nullptr, w->halo_counter.p,
+                                             w->halo_ticket.p);
+        wg_halo_wait<<<1, 32, 0, st>>>(w->halo_flags.p, lo ? 1 : 0, hi ? 1 : 0, w->halo_counter.p,
+                                       w->flag.p);
+        w->launches += 2;
+        return;
+    }
+    auto& n = nccl::get();
     nccl_check(n.GroupStart(), "ncclGroupStart");
     if (w->rank > 0) {
         nccl_check(n.Send(a + cnt, cnt, nccl::t_float64, w->rank - 1, w->comm, st), "ncclSend");
@@ -445,18 +490,28 @@ void enqueue_step(wvb_wg* w) {
     w->cur ^= 1;
 }
 
+int fetch_flags_raw(wvb_wg* w);
 // flag readback (waveguide.h:100), OR-reduced over ranks
 int fetch_flags(wvb_wg* w) {
+    const int f = fetch_flags_raw(w);
+    if (f & WVB_FLAG_HALO_TIMEOUT) {
+        set_last_error("ghost-plane exchange timed out: a neighbouring rank stopped delivering");
+        throw status_error{WVB_ERR_NCCL};
+    }
+    return f;
+}
+int fetch_flags_raw(wvb_wg* w) {
     if (w->nranks > 1) {
         flag_expand<<<1, 32, 0, w->stream>>>(w->flag.p, w->flag5.p);
-        nccl_check(nccl::get().AllReduce(w->flag5.p, w->flag5.p, 5, nccl::t_int32, nccl::op_max,
+        nccl_check(nccl::get().AllReduce(w->flag5.p, w->flag5.p, 6, nccl::t_int32, nccl::op_max,
                                          w->comm, w->stream),
                    "ncclAllReduce");
-        WVB_CUDA(cudaMemcpyAsync(w->h_flag, w->flag5.p, 5 * sizeof(int), cudaMemcpyDeviceToHost,
+        WVB_CUDA(cudaMemcpyAsync(w->h_flag, w->flag5.p, 6 * sizeof(int), cudaMemcpyDeviceToHost,
                                  w->stream));
         WVB_CUDA(cudaStreamSynchronize(w->stream));
         int f = 0;
         for (int i = 0; i < 5; ++i) f |= (w->h_flag[i] ? 1 : 0) << i;
+        if (w->h_flag[5]) f |= WVB_FLAG_HALO_TIMEOUT;
         return f;
     }
     WVB_CUDA(cudaMemcpyAsync(w->h_flag, w->flag.p, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
@@ -479,6 +534,87 @@ long long local_offset(const wvb_wg* w, uint64_t node, int* owned) {
     if (lz < 0 || lz > w->g.nzl + 1) return -1;
     if (owned) *owned = (lz >= 1 && lz <= w->g.nzl);
     return wg_offset(w->g, x, y, lz);
+}
+
+// Maps the z-neighbours' pressure arrays and flag words into this process (CUDA IPC) so that
+// the per-step exchange is plain stores over NVLink. The IPC handles travel through the NCCL
+// communicator the handle already has (one grouped send/recv with each neighbour, once).
+// Collective over all ranks: either every rank ends up with P2P or none does. Returns false
+// (and leaves a message) when the mapping is impossible, e.g. the ranks share a process.
+struct halo_blob {
+    cudaIpcMemHandle_t p0, p1, flags;
+    int32_t nzl, ok;
+};
+bool setup_p2p(wvb_wg* w) {
+    auto& n = nccl::get();
+    w->halo_flags.alloc(2, true, &w->device_bytes);
+    w->halo_counter.alloc(1, true, &w->device_bytes);
+    w->halo_ticket.alloc(1, true, &w->device_bytes);
+    halo_blob mine{};
+    mine.nzl = w->g.nzl;
+    mine.ok = cudaIpcGetMemHandle(&mine.p0, w->P[0].p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.p1, w->P[1].p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.flags, w->halo_flags.p) == cudaSuccess;
+    if (!mine.ok) {
+        set_last_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dev_buf<halo_blob> d_mine, d_peer;
+    d_mine.upload(&mine, 1);
+    d_peer.alloc(2, true);
+    const bool lo = w->rank > 0, hi = w->rank < w->nranks - 1;
+    nccl_check(n.GroupStart(), "ncclGroupStart");
+    if (lo) {
+        nccl_check(n.Send(d_mine.p, sizeof(halo_blob), nccl::t_uint8, w->rank - 1, w->comm, w->stream), "ncclSend");
+        nccl_check(n.Recv(d_peer.p, sizeof(halo_blob), nccl::t_uint8, w->rank - 1, w->comm, w->stream), "ncclRecv");
+    }
+    if (hi) {
+        nccl_check(n.Send(d_mine.p, sizeof(halo_blob), nccl::t_uint8, w->rank + 1, w->comm, w->stream), "ncclSend");
+        nccl_check(n.Recv(d_peer.p + 1, sizeof(halo_blob), nccl::t_uint8, w->rank + 1, w->comm, w->stream), "ncclRecv");
+    }
+    nccl_check(n.GroupEnd(), "ncclGroupEnd");
+    halo_blob peer[2];
+    WVB_CUDA(cudaMemcpyAsync(peer, d_peer.p, sizeof peer, cudaMemcpyDeviceToHost, w->stream));
+    WVB_CUDA(cudaStreamSynchronize(w->stream));
+    int good = mine.ok;
+    auto open = [&](const halo_blob& b, wvb_wg::peer_t& out) {
+        if (!b.ok) {
+            good = 0;
+            return;
+        }
+        void* q[3] = {nullptr, nullptr, nullptr};
+        const cudaIpcMemHandle_t* h[3] = {&b.p0, &b.p1, &b.flags};
+        for (int i = 0; i < 3 && good; ++i) {
+            const cudaError_t e = cudaIpcOpenMemHandle(&q[i], *h[i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_last_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+                good = 0;
+            }
+        }
+        out.P[0] = static_cast<double*>(q[0]);
+        out.P[1] = static_cast<double*>(q[1]);
+        out.flags = static_cast<unsigned long long*>(q[2]);
+        out.nzl = b.nzl;
+    };
+    if (lo) open(peer[0], w->below);
+    if (hi) open(peer[1], w->above);
+    // all or nothing: min over ranks of `good`
+    dev_buf<int> d_good;
+    d_good.upload(&good, 1);
+    nccl_check(n.AllReduce(d_good.p, d_good.p, 1, nccl::t_int32, nccl::op_min, w->comm, w->stream), "ncclAllReduce");
+    int all_good = 0;
+    WVB_CUDA(cudaMemcpyAsync(&all_good, d_good.p, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    WVB_CUDA(cudaStreamSynchronize(w->stream));
+    if (!all_good) {
+        for (wvb_wg::peer_t* p : {&w->below, &w->above}) {
+            for (void* q : {(void*)p->P[0], (void*)p->P[1], (void*)p->flags}) {
+                if (q) cudaIpcCloseMemHandle(q);
+            }
+            *p = wvb_wg::peer_t{};
+        }
+        if (good) set_last_error("another rank could not map its neighbours' memory");
+    }
+    return all_good != 0;
 }
 
 void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
@@ -621,8 +757,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     WVB_CUDA(cudaStreamCreateWithPriority(&w->stream_c, cudaStreamNonBlocking, prio_hi));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_faces, cudaEventDisableTiming));
     WVB_CUDA(cudaEventCreateWithFlags(&w->ev_comm, cudaEventDisableTiming));
-    // measured neutral at N = 2 (0.5898 vs 0.5892 ms/step: the exchange costs ~13 us and the two
-    // extra launches + events about as much), so off by default; WVB_WG_OVERLAP_COMM=1 enables it
+    // faces first + exchange underneath the interior update: WVB_WG_HALO_OVERLAP in desc.flags
     w->overlap_comm = env_int("WVB_WG_OVERLAP_COMM", 0);
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 4);
@@ -647,9 +782,11 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
 
     // ---- kernel variant + launch shape ----------------------------------------------
     int want = d->flags & 0xff;
+#ifdef WVB_DEBUG_KNOBS
     const char* ev = getenv("WVB_WG_KERNEL");
     if (ev && !strcmp(ev, "direct")) want = WVB_WG_KERNEL_DIRECT;
     if (ev && !strcmp(ev, "tma")) want = WVB_WG_KERNEL_TMA;
+#endif
     const bool tma_fits = dx >= 132 && dy >= 10;
     if (want == WVB_WG_KERNEL_AUTO) want = tma_fits ? WVB_WG_KERNEL_TMA : WVB_WG_KERNEL_DIRECT;
     w->variant = want;
@@ -659,7 +796,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->pf = env_int("WVB_WG_PF", 4);
     w->minb = 1;
     w->step_counter.alloc(1, true, &w->device_bytes);
-    w->use_graph = env_int("WVB_WG_GRAPH", 1) && d->nranks == 1;
+    w->use_graph = env_int("WVB_WG_GRAPH", 1);  // switched off below if the exchange goes through NCCL
     int slots;
     long long tiles;
     if (w->variant == WVB_WG_KERNEL_TMA) {
@@ -698,6 +835,25 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         nccl::unique_id id;
         memcpy(&id, d->nccl_unique_id, sizeof id);
         nccl_check(nccl::get().CommInitRank(&w->comm, w->nranks, id, w->rank), "ncclCommInitRank");
+        const uint32_t want_halo = d->flags & (3u << 28);
+        w->halo = wvb_wg::HALO_NCCL;
+        if (want_halo != WVB_WG_HALO_NCCL && env_int("WVB_WG_P2P", 1)) {
+            const bool ok = setup_p2p(w);
+            WVB_REQUIRE(ok || want_halo != WVB_WG_HALO_P2P, WVB_ERR_UNSUPPORTED,
+                        "WVB_WG_HALO_P2P requested but the neighbours' memory cannot be mapped: %s",
+                        g_last_error.c_str());
+            if (ok) w->halo = wvb_wg::HALO_P2P;
+        }
+        // Faces first + exchange underneath the interior update: asked for explicitly, or chosen
+        // for the peer-to-peer transport on slabs large enough that two extra launches are noise
+        // (measured at N = 2, 512^3 per GPU: 0.5670 ms/step against 0.5738 without, 0.5808 NCCL)
+        if (d->flags & WVB_WG_HALO_OVERLAP) w->overlap_comm = 1;
+        if (want_halo == WVB_WG_HALO_AUTO && w->halo == wvb_wg::HALO_P2P &&
+            (long long)g.dx * g.dy * g.nzl >= (4ll << 20) && g.nzl >= 16) {
+            w->overlap_comm = 1;
+        }
+        // NCCL calls are kept out of stream capture: the per-step graph needs the P2P exchange
+        if (w->halo != wvb_wg::HALO_P2P) w->use_graph = 0;
     }
     WVB_CUDA(cudaDeviceSynchronize());
 }
@@ -1151,6 +1307,7 @@ wvb_status wvb_wg_get_info(wvb_wg* w, wvb_wg_info* info) {
     info->tile[1] = w->variant == WVB_WG_KERNEL_TMA ? w->ty : 8;
     info->tile[2] = w->zchunks;
     info->sm_count = w->sm_count;
+    info->halo = w->halo | ((w->nranks > 1 && w->overlap_comm && w->g.nzl >= 3) ? 4 : 0);
     return WVB_OK;
 }
 

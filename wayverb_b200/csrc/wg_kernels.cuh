@@ -782,10 +782,86 @@ __global__ void wg_gather(const double* __restrict__ cur, const long long* __res
     if (i < n) out[(size_t)(*step_ptr) * n + i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
 }
 __global__ void wg_advance(uint32_t* __restrict__ step_ptr) { *step_ptr += 1; }
+
+// ---------------------------------------------------------------------------
+// Ghost-plane exchange over peer-mapped memory (NVLink / NVSwitch), no NCCL call per step.
+// After a step every rank stores its first and last owned plane of the array it just wrote
+// straight into the ghost planes of its z-neighbours (their arrays are mapped into this
+// process with CUDA IPC), then publishes "exchange k delivered" in a flag word that lives in
+// the neighbour's memory (st.release.sys after a system-scope fence by every storing thread
+// and a last-block ticket). wg_halo_wait spins (ld.acquire.sys) on the two flag words the
+// neighbours write into THIS rank's memory before the next step may read the ghost planes.
+// Why one flag per direction is enough: rank r starts exchange k only after its step k
+// kernels have finished, i.e. after it has read its ghost planes for that step; and it starts
+// step k+1 (whose exchange overwrites the ghost planes its neighbours read in step k+1 ... of
+// the OTHER array) only after both neighbours delivered exchange k, which they do after their
+// own step k kernels. The two pressure arrays alternate, so the array written in step k+1 was
+// last read in step k, which every neighbour has provably finished.
+// The exchange counter lives in device memory so that a captured CUDA graph can be replayed.
+// ---------------------------------------------------------------------------
+constexpr int WVB_FLAG_HALO_TIMEOUT = 1 << 30;  // internal bit of the device error flag
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// src_* : this rank's first / last owned plane; dst_* : the neighbours' ghost planes (null at
+// the mesh ends); n16 = 16-byte words per plane
+__global__ void __launch_bounds__(256)
+wg_halo_push(const float4* __restrict__ src_lo, float4* __restrict__ dst_lo,
+             const float4* __restrict__ src_hi, float4* __restrict__ dst_hi, uint32_t n16,
+             unsigned long long* peer_flag_lo, unsigned long long* peer_flag_hi,
+             unsigned long long* __restrict__ counter, unsigned int* __restrict__ ticket) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        if (dst_lo) dst_lo[i] = src_lo[i];
+        if (dst_hi) dst_hi[i] = src_hi[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {  // every block's stores are visible system-wide
+            *ticket = 0;
+            const unsigned long long k = *counter + 1;
+            *counter = k;
+            __threadfence_system();
+            if (peer_flag_lo) st_release_sys(peer_flag_lo, k);
+            if (peer_flag_hi) st_release_sys(peer_flag_hi, k);
+        }
+    }
+}
+
+// flags[0] is written by the neighbour below, flags[1] by the neighbour above
+__global__ void wg_halo_wait(const unsigned long long* __restrict__ flags, int has_lo, int has_hi,
+                             const unsigned long long* __restrict__ counter, int* __restrict__ err) {
+    const int i = threadIdx.x;
+    if (i >= 2 || !(i == 0 ? has_lo : has_hi)) return;
+    const unsigned long long k = *counter;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flags + i) < k) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > 20ull * 1000 * 1000 * 1000) {  // a neighbour died: do not hang
+            atomicOr(err, WVB_FLAG_HALO_TIMEOUT);
+            return;
+        }
+    }
+}
 // error flag -> one int per bit, so that ranks can max-reduce it
 __global__ void flag_expand(const int* __restrict__ flag, int* __restrict__ out5) {
     const int i = threadIdx.x;
     if (i < 5) out5[i] = (*flag >> i) & 1;
+    if (i == 5) out5[5] = (*flag >> 30) & 1;  // WVB_FLAG_HALO_TIMEOUT
 }
 // owned planes of `cur` -> dense float array (x fastest, no padding)
 __global__ void wg_to_f32(const double* __restrict__ cur, float* __restrict__ out, WgGeom g) {

@@ -274,7 +274,8 @@ class Waveguide:
                 "boundary_nodes": tuple(i.boundary_nodes), "device_bytes": i.device_bytes,
                 "kernel_launches": i.kernel_launches,
                 "kernel_variant": {1: "direct", 2: "tma"}.get(i.kernel_variant, "?"),
-                "tile": tuple(i.tile), "sm_count": i.sm_count}
+                "tile": tuple(i.tile), "sm_count": i.sm_count,
+                "halo": {0: "none", 1: "nccl", 2: "p2p"}.get(i.halo & 3, "?") + ("+overlap" if i.halo & 4 else "")}
 
 
 # ---- stock processors ------------------------------------------------------------
