@@ -243,7 +243,8 @@ def test_overlay_reference_processors_drive_waveguide_run(soft):
     want = []
     for s in range(steps):
         if soft:
-            sim.write(src, float(np.float32(sim.read(src))) + float(sig[s]))
+            # cl_float + float sample: a float addition (soft_source.h:21-23)
+            sim.write(src, float(np.float32(sim.read(src)) + np.float32(sig[s])))
         else:
             sim.write(src, float(sig[s]))
         want.append(np.float32(sim.read(rcv)))
