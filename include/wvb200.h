@@ -391,6 +391,43 @@ wvb_status wvb_obj_parse(const char* text, uint64_t length, wvb_float3* vertices
                          wvb_triangle* triangles, uint64_t* num_triangles, char* material_names,
                          uint64_t* material_names_length);
 
+/* ---- post-processing of the ray path's histogram ---------------- */
+typedef struct {
+    double speed_of_sound;        /* environment.speed_of_sound                                  */
+    double acoustic_impedance;    /* environment.acoustic_impedance                              */
+    double room_volume;           /* m^3 (raytracer::postprocess's room_volume)                  */
+    double histogram_sample_rate; /* rate of the energy histogram (1000 Hz in the engine)        */
+    double output_sample_rate;    /* rate of the dirac sequence = of the output signal           */
+    double max_time;              /* seconds; 0 = n_bins / histogram_sample_rate                 */
+    uint64_t seed;                /* Philox seed (the reference seeds from std::random_device)    */
+    int32_t device;
+    int32_t pad_;
+} wvb_pp_params;
+/* generate_dirac_sequence (raytracer/src/stochastic/postprocessing.cpp:29-50): a Poisson process
+ * whose rate grows as 4 pi c^3 t^2 / V (capped at 10000 events/s), starting at t0; sample
+ * floor(t rate) of the sequence gets +1 or -1. Generated on the device. Two-pass (out == NULL
+ * returns the length ceil(max_time * sample_rate) in *count); *events = events drawn. */
+wvb_status wvb_pp_dirac_sequence(const wvb_pp_params* params, double sample_rate, double max_time, float* out,
+                                 uint64_t capacity, uint64_t* count, uint32_t* events);
+/* stochastic::postprocessing (postprocessing.cpp:57-112): the dirac sequence weighted by the
+ * histogram ([n_bins][8] doubles, what wvb_rt_read_histogram returns) so that every histogram
+ * bin's energy is carried by the events inside it (intensity -> pressure per band), filtered by
+ * the 8-band filter bank (frequency_domain/multiband_filter.h:49-93 with hrtf/multiband.h's
+ * bands, 20 Hz - 20 kHz) and mixed down to one signal of
+ * min(ceil(max_time rate), n_bins rate / histogram_rate) samples. Two-pass like above.
+ * weighted_out (optional, [count][8] floats): the weighted sequence before filtering. */
+wvb_status wvb_pp_stochastic(const double* histogram, uint32_t n_bins, const wvb_pp_params* params, float* out,
+                             uint64_t capacity, uint64_t* count, float* weighted_out);
+/* core::multiband_filter_and_mixdown (core/mixdown.h:17-24) of [length][8] floats */
+wvb_status wvb_pp_multiband_mixdown(const float* multiband, uint64_t length, double sample_rate, int32_t device,
+                                    float* out);
+/* combined::postprocess's join (combined/postprocess.h:33-60,104-134): low-pass `lo` (the
+ * waveguide signal) and high-pass `hi` (the ray signal) at the normalised frequency `cutoff`
+ * with relative crossover width `width`, sum them over max(n_lo, n_hi) samples, and fade the
+ * first window_length samples in with the left half of a Hann window. */
+wvb_status wvb_pp_crossover(const float* lo, uint64_t n_lo, const float* hi, uint64_t n_hi, double cutoff,
+                            double width, uint64_t window_length, int32_t device, float* out, uint64_t capacity);
+
 /* ---- mesh construction (the step before waveguide::run) ---------------------- */
 
 typedef struct wvb_mesh wvb_mesh;

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(decl):
         assert hasattr(L, name), "libwvb200.so does not export " + name
     assert L.wvb_version() == 100
-    for name in _lib.WG_SYMBOLS + _lib.RT_SYMBOLS + _lib.MESH_SYMBOLS + _lib.IS_SYMBOLS + _lib.LRS_SYMBOLS:
+    for name in (_lib.WG_SYMBOLS + _lib.RT_SYMBOLS + _lib.MESH_SYMBOLS + _lib.IS_SYMBOLS + _lib.LRS_SYMBOLS +
+                 _lib.SCENE_SYMBOLS + _lib.PP_SYMBOLS):
         assert name in decl
 
 

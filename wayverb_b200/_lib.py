@@ -64,6 +64,14 @@ class WgInfo(C.Structure):
     ]
 
 
+class PpParams(C.Structure):
+    _fields_ = [
+        ("speed_of_sound", C.c_double), ("acoustic_impedance", C.c_double), ("room_volume", C.c_double),
+        ("histogram_sample_rate", C.c_double), ("output_sample_rate", C.c_double), ("max_time", C.c_double),
+        ("seed", C.c_uint64), ("device", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
 class RtSceneDesc(C.Structure):
     _fields_ = [
         ("voxel_index", C.c_void_p), ("voxel_index_count", C.c_uint64),
@@ -123,6 +131,7 @@ RT_SYMBOLS = [
 ]
 
 SCENE_SYMBOLS = ["wvb_voxelise", "wvb_obj_parse"]
+PP_SYMBOLS = ["wvb_pp_dirac_sequence", "wvb_pp_stochastic", "wvb_pp_multiband_mixdown", "wvb_pp_crossover"]
 
 _lib = None
 
@@ -207,6 +216,11 @@ def lib():
     L.wvb_is_results.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64 * 4), C.POINTER(C.c_float)]
     L.wvb_voxelise.argtypes = [vp, u32, vp, u32, u32, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
                                vp, u64, C.POINTER(u64)]
+    L.wvb_pp_dirac_sequence.argtypes = [C.POINTER(PpParams), C.c_double, C.c_double, vp, u64, C.POINTER(u64),
+                                        C.POINTER(u32)]
+    L.wvb_pp_stochastic.argtypes = [vp, u32, C.POINTER(PpParams), vp, u64, C.POINTER(u64), vp]
+    L.wvb_pp_multiband_mixdown.argtypes = [vp, u64, C.c_double, i32, vp]
+    L.wvb_pp_crossover.argtypes = [vp, u64, vp, u64, C.c_double, C.c_double, u64, i32, vp, u64]
     L.wvb_obj_parse.argtypes = [C.c_char_p, u64, vp, C.POINTER(u64), vp, C.POINTER(u64), vp, C.POINTER(u64)]
     _lib = L
     return L

@@ -11,8 +11,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("WVB_LIB_OUT") or os.path.join(HERE, "libwvb200.so")
-SOURCES = ["wg_host.cu", "rt_host.cu", "mesh_host.cu", "is_host.cu", "lrs_design.cpp", "scene_host.cpp"]
-HEADERS = ["common.h", "nccl_dyn.h", "wg_kernels.cuh", "rt_kernels.cuh", "mesh_kernels.cuh", "is_kernels.cuh",
+SOURCES = ["wg_host.cu", "rt_host.cu", "mesh_host.cu", "is_host.cu", "lrs_design.cpp", "scene_host.cpp", "pp_host.cu"]
+HEADERS = ["common.h", "nccl_dyn.h", "wg_kernels.cuh", "rt_kernels.cuh", "mesh_kernels.cuh", "is_kernels.cuh", "pp_kernels.cuh",
            os.path.join("..", "..", "include", "wvb200.h")]
 
 NVCC_FLAGS = [
