@@ -436,8 +436,8 @@ typedef struct wvb_mesh wvb_mesh;
  *   set_node_inside           mesh_setup_program.cpp:110-140 (voxel_inside, 32 probe rays)
  *   set_node_boundary_type    mesh_setup_program.cpp:142-172
  *   compute_boundary_index_data   boundary_coefficient_finder.cpp:39-132 with the
- *       1d (closest triangle, brute force), 2d and 3d finders of
- *       boundary_coefficient_program.cpp:310-484
+ *       1d (closest triangle: the triangle slow_closest_triangle would pick, found through
+ *       the voxel grid), 2d and 3d finders of boundary_coefficient_program.cpp:310-484
  * for the mesh_descriptor {min_corner, dim, spacing} (mesh_descriptor.h:14-20).
  * scene: the voxelised scene (may be NULL when both `inside` and `surface_1d` are
  * given). inside (optional): one byte per node, replaces set_node_inside.

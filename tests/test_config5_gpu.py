@@ -55,6 +55,37 @@ def test_ray_loop_and_image_sources_match_oracle(subdiv, n):
     assert np.array_equal(got_i.view(np.uint8), want_i.view(np.uint8))
 
 
+def test_closest_triangle_through_the_voxel_grid_equals_brute_force():
+    """boundary_coefficient_finder_1d on the 20 608-triangle hall with one surface PER TRIANGLE
+    (so the surface index returned names the triangle picked): the device's voxel-grid search
+    against the oracle's slow_closest_triangle over all triangles, node for node"""
+    from oracle import wgo
+    sc, meta = scene.concert_hall(3)
+    n_tri = sc.triangles.size
+    tri = sc.triangles.copy()
+    tri["surface"] = np.arange(n_tri, dtype=np.uint32)
+    surf = np.repeat(sc.surfaces[:1], n_tri)
+    sc2 = scene.Scene(sc.vertices, tri, surf, pad=0.1, voxeliser="octree", depth=5)
+    spacing = 1.1
+    lo, hi = sc2.aabb[:3] + 0.1, sc2.aabb[3:] - 0.1
+    dims = tuple(int(np.ceil((hi[k] - lo[k]) / spacing)) + 5 for k in range(3))
+    mc = (lo - 2 * spacing).astype(np.float32)
+    coeffs = [wgo.to_flat(0.25)] * n_tri
+    with wvb.RayTracer(sc2) as g:
+        m = wvb.build_mesh(dims, mc, spacing, coeffs, scene=g)
+    o = rto.Scene(sc2)
+    want_inside = o.nodes_inside(mc, dims, spacing)
+    z, y, x = np.indices(want_inside.shape)
+    pts = np.stack([mc[0] + x.astype(np.float32) * np.float32(spacing), mc[1] + y.astype(np.float32) * np.float32(spacing),
+                    mc[2] + z.astype(np.float32) * np.float32(spacing)], -1).reshape(-1, 3)
+    surf_o, _ = o.closest_surface(pts)
+    om = wgo.mesh_from_inside(want_inside, coeffs, surf_o)
+    assert np.array_equal(m.nodes, om.nodes)
+    assert m.b[0].shape[0] > 1000
+    assert np.array_equal(m.b[0], om.b1) and np.array_equal(m.b[1], om.b2) and np.array_equal(m.b[2], om.b3)
+    assert len(set(m.b[0].ravel().tolist())) > 500       # many different triangles were picked
+
+
 def test_mesh_of_the_hall_matches_oracle_and_steps():
     """the 1 kHz-cutoff waveguide of config 5 at a coarser spacing (the full 1 kHz mesh is
     bench-sized): classification + boundary indices on the device == oracle, and the mesh runs"""

@@ -8,16 +8,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-os.environ.setdefault("WVB_WG_KERNEL", sys.argv[1] if len(sys.argv) > 1 else "tma")
 import wayverb_b200 as wvb  # noqa: E402
 from wayverb_b200 import _lib  # noqa: E402
+
+KERNEL = {"tma": _lib.KERNEL_TMA, "direct": _lib.KERNEL_DIRECT}[sys.argv[1] if len(sys.argv) > 1 else "tma"]
 
 s = json.load(open(os.path.join(ROOT, "tests", "golden", "lrs_coefficients.json")))["sets"][0]["impedance"]
 c = np.zeros((), _lib.COEFF_DT)
 c["b"], c["a"] = s["b"], s["a"]
 dims = (512, 512, 512)
 m = wvb.cuboid_mesh(dims, [c])
-with wvb.Waveguide(m) as g:
+with wvb.Waveguide(m, kernel=KERNEL) as g:
     g.write(m.index(256, 256, 256), 1.0)
     assert g.step(int(sys.argv[2]) if len(sys.argv) > 2 else 6) == 0
     print(g.info())

@@ -133,7 +133,12 @@ wvb_status wvb_mesh_create(wvb_rt* scene, const float min_corner[3], const int32
             dev_buf<uint32_t> d_list;
             d_list.upload(list1.data(), list1.size());
             d_idx1.alloc(n1r, false);
-            mesh::mesh_find_1d<<<(n1r + 63) / 64, 64>>>(*scp, d, d_list.p, n1r, d_idx1.p);
+            // brute force for a handful of triangles, the voxel search otherwise: same answer
+            if (scp->n_triangles <= 48) {
+                mesh::mesh_find_1d<false><<<(n1r + 63) / 64, 64>>>(*scp, d, d_list.p, n1r, d_idx1.p);
+            } else {
+                mesh::mesh_find_1d<true><<<(n1r + 63) / 64, 64>>>(*scp, d, d_list.p, n1r, d_idx1.p);
+            }
             WVB_CUDA(cudaGetLastError());
         }
         std::vector<uint32_t> idx1(n1r);

@@ -314,8 +314,18 @@ __device__ __forceinline__ float point_triangle_distance_squared(const rt::TriPr
 }
 
 // boundary_coefficient_finder_1d (boundary_coefficient_program.cpp:310-343) for the
-// compacted list of 1-d / reentrant nodes: surface of the closest triangle by brute
-// force (slow_closest_triangle, :222-241; first minimum wins).
+// compacted list of 1-d / reentrant nodes: surface of the closest triangle.
+//
+// The reference's kernel calls slow_closest_triangle (:222-241): every triangle, first minimum
+// wins, O(nodes x triangles). VOXEL = true gives the SAME triangle through the voxel grid (the
+// search the reference sketches at :243-308, made exact): voxels overlapping the box
+// [pt - r, pt + r] are scanned, r doubling from half a voxel; as soon as the best distance found
+// is <= r the answer is final, because every triangle at that distance or closer touches the
+// ball of that radius, which lies inside the scanned box, and voxel lists name every triangle
+// that overlaps them (the precondition of wvb_rt_scene_desc). Ties go to the lowest triangle
+// index, which is what "first minimum wins" yields over the whole array, and distances come
+// from the same point_triangle_distance_squared, so the result is identical, not just close.
+template <bool VOXEL>
 static __global__ void mesh_find_1d(rt::Scene sc, Desc d, const uint32_t* __restrict__ node_list, uint32_t n,
                              uint32_t* __restrict__ surface_out) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,11 +334,44 @@ static __global__ void mesh_find_1d(rt::Scene sc, Desc d, const uint32_t* __rest
     const f3 pt = node_position(d, node_list[k], x, y, z);
     uint32_t best = 0;
     float distance = INFINITY;
-    for (uint32_t i = 0; i != sc.n_triangles; ++i) {
-        const float nd = point_triangle_distance_squared(sc.pre[i], pt);
-        if (nd < distance) {
-            best = i;
-            distance = nd;
+    if (!VOXEL) {
+        for (uint32_t i = 0; i != sc.n_triangles; ++i) {
+            const float nd = point_triangle_distance_squared(sc.pre[i], pt);
+            if (nd < distance) {
+                best = i;
+                distance = nd;
+            }
+        }
+    } else {
+        const int side = (int)sc.side;
+        const float vx = (sc.c1.x - sc.c0.x) / (float)side, vy = (sc.c1.y - sc.c0.y) / (float)side,
+                    vz = (sc.c1.z - sc.c0.z) / (float)side;
+        float r = 0.5f * fminf(vx, fminf(vy, vz));
+        // the whole grid is inside this radius of any point that matters; beyond it every voxel is scanned
+        const float r_all = 2.0f * (fabsf(pt.x - sc.c0.x) + fabsf(pt.y - sc.c0.y) + fabsf(pt.z - sc.c0.z) +
+                                    (sc.c1.x - sc.c0.x) + (sc.c1.y - sc.c0.y) + (sc.c1.z - sc.c0.z));
+        for (;;) {
+            // voxel range overlapping [pt - r, pt + r], one voxel of slack for rounding, clamped
+            const int x0 = max(0, (int)floorf((pt.x - r - sc.c0.x) / vx) - 1), x1 = min(side - 1, (int)floorf((pt.x + r - sc.c0.x) / vx) + 1);
+            const int y0 = max(0, (int)floorf((pt.y - r - sc.c0.y) / vy) - 1), y1 = min(side - 1, (int)floorf((pt.y + r - sc.c0.y) / vy) + 1);
+            const int z0 = max(0, (int)floorf((pt.z - r - sc.c0.z) / vz) - 1), z1 = min(side - 1, (int)floorf((pt.z + r - sc.c0.z) / vz) + 1);
+            for (int ix = x0; ix <= x1; ++ix) {
+                for (int iy = y0; iy <= y1; ++iy) {
+                    for (int iz = z0; iz <= z1; ++iz) {
+                        const uint2 cell = sc.cells[((size_t)ix * side + iy) * side + iz];
+                        for (uint32_t e = 0; e != cell.y; ++e) {
+                            const rt::VoxEntry& ve = sc.entries[cell.x + e];
+                            const float nd = point_triangle_distance_squared(ve.pre, pt);
+                            if (nd < distance || (nd == distance && ve.tri < best)) {
+                                best = ve.tri;
+                                distance = nd;
+                            }
+                        }
+                    }
+                }
+            }
+            if (distance <= r * r || r > r_all) break;
+            r *= 2.0f;
         }
     }
     surface_out[k] = sc.triangles[best].surface;

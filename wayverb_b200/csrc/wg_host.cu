@@ -108,6 +108,7 @@ struct wvb_wg {
     int overlap = 1;
     int bminb = 4;
     int bpipe = 4;  // >0: pipelined 1-d boundary walk with this many blocks per SM
+    int bthreads = 128;
     int air_first = 1;
     dev_buf<uint32_t> step_counter;
     int use_graph = 1;
@@ -370,6 +371,22 @@ void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t 
         auto& l = w->bl[k];
         return BList{l.n, l.off.p, l.meta.p, l.ci.p, l.mem.p};
     };
+    // Placement experiments of round 2 (profiles/r02_experiments.md): the boundary kernel does not
+    // co-reside with the air kernel because an SM cannot change its L1 / shared-memory split while
+    // a CTA is resident (air: 164 KB split, boundary: none). Giving both the same split makes them
+    // overlap but costs more L1 than the overlap returns (0.563 vs 0.561 ms with the air kernel's
+    // split on the boundary kernel, 0.641 ms with the maximum split on both), and a small-footprint
+    // boundary kernel resident for the whole step is slower still (0.63-0.71 ms). The step already
+    // runs at 96 % of the DRAM roofline of its summed traffic, so the plain sequence stays.
+#ifdef WVB_DEBUG_KNOBS
+    static int carveout_set = -1;
+    const int carve = env_int("WVB_WG_BCARVE", -1);
+    if (carveout_set != carve && carve >= 0) {
+        WVB_CUDA(cudaFuncSetAttribute(wg_boundary_all<THREADS, MINB, PIPE>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        carveout_set = carve;
+    }
+#endif
     wg_boundary_all<THREADS, MINB, PIPE><<<nb1 + nb2 + nb3, T, 0, st>>>(
             cur, prev, L(0), L(1), L(2), nb1, nb2, w->coeffs.p, w->g, w->courant, w->courant_sq,
             w->flag.p);
@@ -377,7 +394,10 @@ void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t 
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
-    if (w->bpipe > 0) {
+    if (w->bthreads == 64 && w->bpipe > 0) {
+        // two warps with up to 128 registers each: small enough to sit next to three air CTAs
+        launch_boundary_t<64, 8, true>(w, cur, prev, st);
+    } else if (w->bpipe > 0) {
         if (w->bminb >= 6) launch_boundary_t<128, 6, true>(w, cur, prev, st);
         else if (w->bminb == 5) launch_boundary_t<128, 5, true>(w, cur, prev, st);
         else if (w->bminb == 4) launch_boundary_t<128, 4, true>(w, cur, prev, st);
@@ -762,6 +782,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->overlap = env_int("WVB_WG_OVERLAP", 1);
     w->bminb = env_int("WVB_WG_BMINB", 4);
     w->bpipe = env_int("WVB_WG_BPIPE", 4);
+    w->bthreads = env_int("WVB_WG_BTHREADS", 128);
     w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
