@@ -339,10 +339,13 @@ size_t run(const core::compute_context& cc,
 /// The same loop for the stock processors, executed on the device in one call
 /// (wvb_wg_run): hard/soft source at one node, postprocessor::node at each
 /// receiver. out[step * receivers.size() + r].
+namespace detail {
+inline int32_t poll_keep_going(void* user) { return static_cast<const std::atomic_bool*>(user)->load() ? 1 : 0; }
+}  // namespace detail
 inline size_t run_stock(const core::compute_context& cc, const mesh& mesh, size_t source_node,
                         const util::aligned::vector<double>& signal, bool soft,
                         const util::aligned::vector<size_t>& receivers,
-                        util::aligned::vector<double>& out) {
+                        util::aligned::vector<double>& out, const std::atomic_bool* keep_going = nullptr) {
     const detail::handle h{cc, mesh};
     util::aligned::vector<uint64_t> rcv(receivers.begin(), receivers.end());
     out.assign(signal.size() * receivers.size(), 0.0);
@@ -355,6 +358,10 @@ inline size_t run_stock(const core::compute_context& cc, const mesh& mesh, size_
     p.n_receivers = uint32_t(rcv.size());
     p.out = out.data();
     p.check_interval = 64;
+    // polled every 64 steps: the reference tests keep_going every step (waveguide.h:80) and
+    // returns the steps completed so far
+    p.keep_going = keep_going ? &detail::poll_keep_going : nullptr;
+    p.keep_going_user = const_cast<std::atomic_bool*>(keep_going);
     uint32_t done = 0;
     int32_t flags = 0;
     core::detail::check(wvb_wg_run(h.get(), &p, &done, &flags));
@@ -658,7 +665,7 @@ inline bool canonical_impl(const core::compute_context& cc, const mesh& mesh, do
     for (auto n : compute_neighbors(mesh.get_descriptor(), rcv)) nodes.push_back(n);
     const util::aligned::vector<double> signal(input.begin(), input.end());
     util::aligned::vector<double> gathered;
-    const auto steps = run_stock(cc, mesh, checked_node(mesh, source), signal, false, nodes, gathered);
+    const auto steps = run_stock(cc, mesh, checked_node(mesh, source), signal, false, nodes, gathered, &keep_going);
     if (double(steps) != ideal_steps) return false;
     out.sample_rate = sample_rate;
     out.directional.clear();

@@ -196,7 +196,9 @@ wvb_status wvb_wg_swap(wvb_wg* wg);
  *          i.e. p(step) including the injected sample.
  * Receivers a rank does not own are written as 0 (sum over ranks = full trace).
  * *steps_done = n_steps unless an error flag stopped the run (checked every
- * `check_interval` steps; 0 = only at the end). */
+ * `check_interval` steps; 0 = only at the end) or the caller cancelled it: keep_going
+ * (optional) is polled at the same interval, like `&& keep_going` in the reference's loop
+ * condition (waveguide.h:80), and a zero return ends the run after the steps done so far. */
 typedef struct {
     uint64_t source_node;
     const double* signal;
@@ -206,6 +208,8 @@ typedef struct {
     uint32_t n_receivers;
     double* out;
     uint32_t check_interval;
+    int32_t (*keep_going)(void* user); /* may be NULL */
+    void* keep_going_user;
 } wvb_wg_run_params;
 wvb_status wvb_wg_run(wvb_wg* wg, const wvb_wg_run_params* p, uint32_t* steps_done,
                       int32_t* error_flags);

@@ -81,6 +81,17 @@ static int canonical_run(double b0) {
     }
     std::atomic_bool stop{false};
     if (!canonical(cc, m, source, receiver, env, 500.0, seconds, stop, no_pressure_callback{}).empty()) return 14;
+    // cancellation DURING the device-side run: keep_going is polled every 64 steps (the reference
+    // polls every step, waveguide.h:80) and the run returns the steps completed so far
+    {
+        util::aligned::vector<double> signal(300, 0.0), out;
+        signal[0] = 1.0;
+        const auto src = compute_index(m.get_descriptor(), source);
+        const auto done = run_stock(cc, m, src, signal, false, {src}, out, &stop);
+        if (done != 64) return 15;
+        std::atomic_bool go{true};
+        if (run_stock(cc, m, src, signal, false, {src}, out, &go) != 300) return 16;
+    }
     return 0;
 }
 

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_pod_layouts():
     assert _lib.NODE_DT.itemsize == 8 and _lib.COEFF_DT.itemsize == 112 and _lib.BDATA_DT.itemsize == 56
-    assert C.sizeof(_lib.WgRunParams) == 56
+    assert C.sizeof(_lib.WgRunParams) == 72
     # wvb_is_desc: 2 x float[3], double, 2 x int32, uint64; raytracer::impulse<8> is 64 bytes
     assert C.sizeof(_lib.IsDesc) == 48 and _lib.IsDesc.acoustic_impedance.offset == 24
     assert _lib.IMPULSE_DT.itemsize == 64 and _lib.IMPULSE_DT.fields["distance"][1] == 48

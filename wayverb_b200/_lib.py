@@ -51,6 +51,8 @@ class WgRunParams(C.Structure):
         ("n_receivers", C.c_uint32),
         ("out", C.c_void_p),
         ("check_interval", C.c_uint32),
+        ("keep_going", C.c_void_p),
+        ("keep_going_user", C.c_void_p),
     ]
 
 

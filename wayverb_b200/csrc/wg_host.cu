@@ -1268,12 +1268,13 @@ wvb_status wvb_wg_run(wvb_wg* w, const wvb_wg_run_params* p, uint32_t* steps_don
             if (ci && done < p->n_steps) {
                 flags = fetch_flags(w);
                 if (flags) break;
+                if (p->keep_going && !p->keep_going(p->keep_going_user)) break;  // waveguide.h:80
             }
         }
         WVB_CUDA(cudaGetLastError());
         if (!flags) flags = fetch_flags(w);
-        if (p->n_receivers) {
-            WVB_CUDA(cudaMemcpyAsync(p->out, d_out.p, (size_t)p->n_steps * p->n_receivers * 8,
+        if (p->n_receivers && done) {
+            WVB_CUDA(cudaMemcpyAsync(p->out, d_out.p, (size_t)done * p->n_receivers * 8,
                                      cudaMemcpyDeviceToHost, w->stream));
         }
         WVB_CUDA(cudaStreamSynchronize(w->stream));
