@@ -110,6 +110,10 @@ enum {
 };
 /* bit 30: update the two face planes first and exchange them underneath the interior update */
 #define WVB_WG_HALO_OVERLAP (1u << 30)
+/* bit 31: temporal blocking -- wvb_wg_step / wvb_wg_time_steps advance two steps per pass over
+ * HBM where they can (pairs of plain steps on a single-GPU handle whose planes are at least
+ * 132 x 10 nodes); results are bit-identical to single steps. Costs two more pressure arrays. */
+#define WVB_WG_TEMPORAL2 (1u << 31)
 
 /* What waveguide::run receives through `mesh` (mesh.h:12-26, setup.h:27-85),
  * restricted to the z-slab this handle owns. */

@@ -410,3 +410,57 @@ def test_config2_ten_thousand_steps():
         assert 0.25 < late / early < 4.0, (early, late)
         f = g.field()
         assert np.isfinite(f).all() and np.abs(f).max() < 1.0
+
+
+# ---- temporal blocking: two steps per pass (WVB_WG_TEMPORAL2) --------------------------------------
+@pytest.mark.parametrize("dims,steps", [((140, 24, 14), 60), ((150, 37, 19), 41), ((260, 20, 12), 7), ((133, 11, 9), 2)])
+def test_temporal_blocking_is_bit_identical(dims, steps):
+    """pairs of steps fused into one pass (wg_air_tb2 + shell + two boundary launches) against the
+    oracle's single steps: field and filter memories identical, odd step counts included"""
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [golden_coeffs(0)])
+    src = om.index(dims[0] // 2, dims[1] // 2, dims[2] // 2)
+    o = wgo.Sim(om)
+    o.write(src, 1.0)
+    o.write(om.index(3, 3, 3), -0.5)          # next to a corner: walls, edges and the corner react early
+    assert o.step(steps) == 0
+    with wvb.Waveguide(to_wvb(om), kernel=_lib.KERNEL_TMA, flags=_lib.TEMPORAL2) as g:
+        g.write(src, 1.0)
+        g.write(om.index(3, 3, 3), -0.5)
+        assert g.step(steps) == 0
+        assert_parity(g.field(), o.field(), "field")
+        for n in (1, 2, 3):
+            assert_parity(g.boundary_data(n)["filter_memory"].ravel(), o.boundary_data(n)["mem"].ravel(),
+                          "filter memory %d-d" % n)
+        # and on: a few more calls of mixed length keep the arrays' roles straight
+        for k in (1, 2, 3, 4):
+            assert g.step(k) == 0 and o.step(k) == 0
+        assert_parity(g.field(), o.field(), "field after mixed-length calls")
+        assert g.read(src) == o.read(src)
+
+
+def test_temporal_blocking_l_shaped_room_and_random_field():
+    dz, dy, dx = 14, 30, 150
+    ins = np.zeros((dz, dy, dx), bool)
+    ins[2:dz - 2, 2:dy - 2, 2:70] = True
+    ins[2:dz - 2, 2:14, 2:dx - 2] = True
+    zz, yy, xx = np.indices(ins.shape)
+    surf = ((xx > 60).astype(np.uint32) + (yy > 12).astype(np.uint32)).ravel()
+    om = wgo.mesh_from_inside(ins, [golden_coeffs(0), golden_coeffs(1), golden_coeffs(2)], surf)
+    f0 = np.random.default_rng(7).standard_normal(om.num_nodes)
+    f0[om.nodes["boundary_type"] == 0] = 0.0
+    o = wgo.Sim(om)
+    o.set_field(f0)
+    assert o.step(10) == 0
+    with wvb.Waveguide(to_wvb(om), kernel=_lib.KERNEL_TMA, flags=_lib.TEMPORAL2) as g:
+        g.set_field(f0)
+        assert g.step(10) == 0
+        assert_parity(g.field(), o.field())
+        for n in (1, 2, 3):
+            assert_parity(g.boundary_data(n)["filter_memory"].ravel(), o.boundary_data(n)["mem"].ravel())
+    # error flags survive the fusion: an inf planted next to a wall is reported like the reference does
+    o2 = wgo.Sim(om)
+    o2.write(om.index(30, 8, 7), np.inf)
+    fo = o2.step(4)
+    with wvb.Waveguide(to_wvb(om), kernel=_lib.KERNEL_TMA, flags=_lib.TEMPORAL2) as g:
+        g.write(om.index(30, 8, 7), np.inf)
+        assert g.step(4) == fo and fo != 0

@@ -21,6 +21,7 @@ BDATA_DT = np.dtype([("filter_memory", "<f8", (6,)), ("coefficient_index", "<u4"
 WVB_OK, WVB_ERR_INVALID, WVB_ERR_CUDA, WVB_ERR_NO_DEVICE, WVB_ERR_NCCL, WVB_ERR_UNSUPPORTED, WVB_ERR_SIM = range(7)
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 HALO_AUTO, HALO_NCCL, HALO_P2P, HALO_OVERLAP = 0, 1 << 28, 2 << 28, 1 << 30  # wvb_wg_desc.flags
+TEMPORAL2 = 1 << 31
 
 
 class WgDesc(C.Structure):

@@ -128,6 +128,19 @@ struct wvb_wg {
         unsigned long long* flags = nullptr;       // the neighbour's flag words, mapped here
         int nzl = 0;
     } below, above;
+    // temporal blocking (two steps per pass, wg_air_tb2): two more pressure arrays, a class map
+    // with the extra SHELL class, the list of shell nodes, tensor maps with the wider box
+    struct tb_t {
+        bool on = false;
+        dev_buf<double> T[2];
+        dev_buf<uint8_t> code;
+        dev_buf<uint32_t> shell;
+        uint32_t n_shell = 0;
+        CUtensorMap one[2];  // single-step maps of T[0], T[1]
+        CUtensorMap wide[4]; // TB2 maps of P[0], P[1], T[0], T[1]
+        int zchunks = 1;
+        uint64_t pairs = 0;
+    } tb;
     dev_buf<unsigned long long> halo_flags;    // [0] written by the rank below, [1] by the rank above
     dev_buf<unsigned long long> halo_counter;  // exchanges done
     dev_buf<unsigned int> halo_ticket;
@@ -280,7 +293,9 @@ int pick_zchunks(long long tiles, int nzl, int slots, int min_len) {
     return best;
 }
 
-void make_tensor_map(wvb_wg* w, int which, int ty) {
+void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows);
+void make_tensor_map(wvb_wg* w, int which, int ty) { encode_plane_map(w, &w->map[which], w->P[which].p, ty + 2); }
+void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows) {
     encode_tiled_fn enc = get_encode_tiled();
     WVB_REQUIRE(enc != nullptr, WVB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     const WgGeom& g = w->g;
@@ -288,9 +303,9 @@ void make_tensor_map(wvb_wg* w, int which, int ty) {
     // overhang it are zero-filled by the TMA unit
     cuuint64_t gdim[3] = {(cuuint64_t)g.px, (cuuint64_t)g.py, (cuuint64_t)(g.nzl + 2)};
     cuuint64_t gstr[2] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.plane * 8};
-    cuuint32_t box[3] = {132, (cuuint32_t)(ty + 2), 1};
+    cuuint32_t box[3] = {132, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&w->map[which], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, w->P[which].p, gdim, gstr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WVB_REQUIRE(r == CUDA_SUCCESS, WVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -360,8 +375,8 @@ void launch_air(wvb_wg* w, const double* cur, double* prev) {
     launch_air(w, cur, prev, ZWindow{1, w->g.nzl, w->zchunks});
 }
 
-template <int THREADS, int MINB, bool PIPE>
-void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
+template <int THREADS, int MINB, bool PIPE, bool SEP = false>
+void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t st, double* out = nullptr) {
     const uint32_t n1 = w->bl[0].n, n2 = w->bl[1].n, n3 = w->bl[2].n;
     const uint32_t T = THREADS;
     uint32_t nb1 = (n1 + T - 1) / T;
@@ -382,14 +397,20 @@ void launch_boundary_t(wvb_wg* w, const double* cur, double* prev, cudaStream_t 
     static int carveout_set = -1;
     const int carve = env_int("WVB_WG_BCARVE", -1);
     if (carveout_set != carve && carve >= 0) {
-        WVB_CUDA(cudaFuncSetAttribute(wg_boundary_all<THREADS, MINB, PIPE>,
+        WVB_CUDA(cudaFuncSetAttribute(wg_boundary_all<THREADS, MINB, PIPE, SEP>,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         carveout_set = carve;
     }
 #endif
-    wg_boundary_all<THREADS, MINB, PIPE><<<nb1 + nb2 + nb3, T, 0, st>>>(
+    wg_boundary_all<THREADS, MINB, PIPE, SEP><<<nb1 + nb2 + nb3, T, 0, st>>>(
             cur, prev, L(0), L(1), L(2), nb1, nb2, w->coeffs.p, w->g, w->courant, w->courant_sq,
-            w->flag.p);
+            w->flag.p, out);
+}
+// the boundary update reading `previous` and writing a third array (temporal blocking)
+void launch_boundary_sep(wvb_wg* w, const double* cur, double* prev, double* out, cudaStream_t st) {
+    if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
+    launch_boundary_t<128, 4, true, true>(w, cur, prev, st, out);
+    w->launches++;
 }
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
@@ -508,6 +529,52 @@ void enqueue_launch(wvb_wg* w) {
 void enqueue_step(wvb_wg* w) {
     enqueue_launch(w);
     w->cur ^= 1;
+}
+
+// Two steps in one pass (see wg_air_tb2): A = current, B = previous -> C = p(n+1), D = p(n+2).
+// Afterwards D is `current` and C `previous`: the handle's two arrays trade places with the two
+// scratch arrays (pointers and tensor maps), so everything else keeps addressing P[cur].
+void enqueue_pair(wvb_wg* w) {
+    using Cfg = Tb2Cfg<5>;
+    auto& tb = w->tb;
+    const int ci = w->cur, pi = w->cur ^ 1;
+    double* A = w->P[ci].p;
+    double* B = w->P[pi].p;
+    double* C = tb.T[0].p;
+    double* D = tb.T[1].p;
+    const WgGeom& g = w->g;
+    const bool has_boundary = w->bl[0].n + w->bl[1].n + w->bl[2].n;
+    const int tiles_x = (g.dx + Cfg::TX - 1) / Cfg::TX, tiles_y = (g.dy + Cfg::TY - 1) / Cfg::TY;
+    WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
+    WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
+    wg_air_tb2<Cfg><<<(unsigned)(tiles_x * tiles_y * tb.zchunks), Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
+            tb.wide[ci], B, C, D, tb.code.p, g, tiles_x, tiles_y, tb.zchunks, w->flag.p);
+    w->launches++;
+    if (has_boundary) launch_boundary_sep(w, A, B, C, w->stream_b);  // p(n+1) on the walls
+    WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
+    WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+    // C is complete: shell nodes and the walls' second step, side by side
+    WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
+    WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
+    if (tb.n_shell) {
+        wg_shell<<<(tb.n_shell + 255) / 256, 256, 0, w->stream>>>(C, A, D, tb.shell.p, tb.n_shell, g, w->flag.p);
+        w->launches++;
+    }
+    if (has_boundary) launch_boundary_sep(w, C, A, D, w->stream_b);  // p(n+2) on the walls
+    WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
+    WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+    // current <- D, previous <- C
+    std::swap(w->P[ci].p, tb.T[1].p);
+    std::swap(w->map[ci], tb.one[1]);
+    std::swap(tb.wide[ci], tb.wide[3]);
+    std::swap(w->P[pi].p, tb.T[0].p);
+    std::swap(w->map[pi], tb.one[0]);
+    std::swap(tb.wide[pi], tb.wide[2]);
+    tb.pairs++;
+    if (w->step_graph) {  // captured with the old pointers
+        cudaGraphExecDestroy(w->step_graph);
+        w->step_graph = nullptr;
+    }
 }
 
 int fetch_flags_raw(wvb_wg* w);
@@ -849,6 +916,56 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     const int inner = std::max(1, g.nzl - 2);
     w->zchunks_inner = zc_req > 0 ? std::min(zc_req, inner) : pick_zchunks(tiles, inner, slots, 12);
 
+    // ---- temporal blocking (prototype; one GPU, TMA-sized meshes) ------------------------------
+    if ((d->flags & WVB_WG_TEMPORAL2) || env_int("WVB_WG_TB2", 0)) {
+        WVB_REQUIRE(d->nranks == 1 && tma_fits, WVB_ERR_UNSUPPORTED,
+                    "WVB_WG_TEMPORAL2 needs a single-GPU handle and a mesh of at least 132 x 10 nodes per plane");
+        using Cfg = Tb2Cfg<5>;
+        auto& tb = w->tb;
+        // class map with SHELL = an AIR node with a BOUNDARY node among its six neighbours
+        auto cls_at = [&](int x, int y, int lz) -> int {
+            if (x < 0 || y < 0 || x >= dx || y >= dy || lz < 1 || lz > g.nzl) return CLS_NONE;
+            const uint8_t b = code[(size_t)lz * g.cplane + (size_t)y * g.pc + (x >> 1)];
+            return (x & 1) ? (b >> 4) : (b & 0xf);
+        };
+        std::vector<uint8_t> code_tb(code);
+        std::vector<std::vector<uint32_t>> shell_planes(g.nzl);
+        parallel_for(g.nzl, [&](int64_t lp) {
+            const int lz = (int)lp + 1;
+            for (int y = 0; y < dy; ++y) {
+                for (int x = 0; x < dx; ++x) {
+                    if (cls_at(x, y, lz) != CLS_AIR) continue;
+                    const bool shell = cls_at(x - 1, y, lz) == CLS_BOUNDARY || cls_at(x + 1, y, lz) == CLS_BOUNDARY ||
+                                       cls_at(x, y - 1, lz) == CLS_BOUNDARY || cls_at(x, y + 1, lz) == CLS_BOUNDARY ||
+                                       cls_at(x, y, lz - 1) == CLS_BOUNDARY || cls_at(x, y, lz + 1) == CLS_BOUNDARY;
+                    if (!shell) continue;
+                    uint8_t& cb = code_tb[(size_t)lz * g.cplane + (size_t)y * g.pc + (x >> 1)];
+                    cb = (x & 1) ? (uint8_t)((cb & 0x0f) | (CLS_SHELL << 4)) : (uint8_t)((cb & 0xf0) | CLS_SHELL);
+                    shell_planes[lp].push_back((uint32_t)wg_offset(g, x, y, lz));
+                }
+            }
+        });
+        std::vector<uint32_t> shell;
+        for (auto& v : shell_planes) shell.insert(shell.end(), v.begin(), v.end());
+        tb.n_shell = (uint32_t)shell.size();
+        tb.code.upload(code_tb.data(), code_tb.size(), &w->device_bytes);
+        tb.shell.upload(shell.data(), shell.size(), &w->device_bytes);
+        tb.T[0].alloc((size_t)total, true, &w->device_bytes);
+        tb.T[1].alloc((size_t)total, true, &w->device_bytes);
+        encode_plane_map(w, &tb.one[0], tb.T[0].p, w->ty + 2);
+        encode_plane_map(w, &tb.one[1], tb.T[1].p, w->ty + 2);
+        double* arr[4] = {w->P[0].p, w->P[1].p, tb.T[0].p, tb.T[1].p};
+        for (int i = 0; i < 4; ++i) encode_plane_map(w, &tb.wide[i], arr[i], Cfg::TY + 4);
+        WVB_CUDA(cudaFuncSetAttribute(wg_air_tb2<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::SMEM_BYTES));
+        int occ = 0;
+        WVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wg_air_tb2<Cfg>, Cfg::THREADS, Cfg::SMEM_BYTES));
+        const long long tb_tiles = (long long)((dx + Cfg::TX - 1) / Cfg::TX) * ((dy + Cfg::TY - 1) / Cfg::TY);
+        const int tb_zc = env_int("WVB_WG_TB2_ZCHUNKS", 0);
+        tb.zchunks = tb_zc > 0 ? std::min(tb_zc, g.nzl) : pick_zchunks(tb_tiles, g.nzl, std::max(1, occ) * w->sm_count, 24);
+        tb.on = true;
+    }
+
     // ---- NCCL ---------------------------------------------------------------------------
     if (w->nranks > 1) {
         WVB_REQUIRE(d->nccl_unique_id != nullptr, WVB_ERR_INVALID, "nranks > 1 needs an ncclUniqueId");
@@ -918,6 +1035,9 @@ cudaGraphExec_t capture_two_steps(wvb_wg* w, Body&& body) {
 
 // n plain steps, through the two-step graph where possible
 void enqueue_steps(wvb_wg* w, uint32_t n) {
+    if (w->tb.on) {
+        for (; n >= 2; n -= 2) enqueue_pair(w);
+    }
     const uint64_t per_step = 1 + ((w->bl[0].n + w->bl[1].n + w->bl[2].n) ? 1 : 0);
     if (w->use_graph && n >= 4) {
         if (w->cur != 0) {  // the graph is captured for P[0] = current

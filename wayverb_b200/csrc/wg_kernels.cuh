@@ -460,6 +460,254 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
 }
 
 // ---------------------------------------------------------------------------
+// Variant TB2 (temporal blocking, prototype): TWO time steps per pass over HBM.
+//
+// The leapfrog update needs p(n) and p(n-1) to make p(n+1); a CTA that keeps three planes of
+// p(n+1) in shared memory can go on to p(n+2) = S(p(n+1)) / 3 - p(n) without a trip to HBM, so a
+// pair of steps costs one read of p(n) and p(n-1) and one write of p(n+1) and p(n+2):
+// 32.5 B per node per pair against 2 x 24.5 B.
+//
+// Same TX x TY column per CTA, same z-march and TMA plane ring as wg_air_tma, with a halo of
+// two: level 0 = p(n) arrives as (TX+4) x (TY+4) boxes; level 1 = p(n+1) is computed for the
+// (TX+2) x (TY+2) inner part of every box (the rim of one is recomputed by the neighbouring
+// CTAs) into a ring of three shared-memory planes and, for the nodes this CTA owns, written to
+// C; level 2 = p(n+2) is computed for the owned nodes from the level-1 ring and written to D.
+// Every value is produced by exactly the arithmetic of update_pair, in the same order, so the
+// result is bit-identical to two single steps.
+//
+// Boundary nodes keep their own kernel (their filter state must advance step by step), which
+// splits the air nodes in two classes: AIR nodes none of whose six neighbours is a boundary
+// node get p(n+2) here; the others ("shell", one layer along every wall) only get p(n+1) here
+// and p(n+2) from wg_shell once the boundary kernel has produced p(n+1) on the walls.
+// Sequence for one pair: {wg_air_tb2 || boundary(A, B -> C)} -> {wg_shell || boundary(C, A -> D)}.
+// ---------------------------------------------------------------------------
+enum : uint8_t { CLS_SHELL = 3 };  // TB2's class map only: AIR with a BOUNDARY neighbour
+
+template <int NSTAGE_>
+struct Tb2Cfg {
+    static constexpr int TX = 128, TY = 8;
+    static constexpr int NSTAGE = NSTAGE_;       // level-0 ring: 3 live planes + prefetch
+    static constexpr int BOXX = TX + 4, BOXY = TY + 4;
+    static constexpr int THREADS = 256;
+    static constexpr int L1_PAIRS = (BOXX / 2) * (TY + 2);          // 66 x 10 = 660
+    static constexpr int L1_PER_THREAD = (L1_PAIRS + THREADS - 1) / THREADS;  // 3
+    static constexpr uint32_t BOX_BYTES = BOXX * BOXY * 8;           // 12 672
+    static constexpr uint32_t STAGE_BYTES = (BOX_BYTES + 127u) & ~127u;
+    static constexpr uint32_t SMEM_BYTES = (NSTAGE + 3) * STAGE_BYTES + NSTAGE * 8 + 128;
+    static_assert(NSTAGE >= 4, "three live level-0 planes + at least one in flight");
+};
+
+// one pair of nodes: v = third(sum of six ports) - p, the arithmetic of update_pair
+__device__ __forceinline__ void tb2_pair(uint32_t sb, uint32_t sm, uint32_t sa, double2 p, double& v0,
+                                         double& v1, double& s0, double& s1) {
+    constexpr uint32_t ROW = Tb2Cfg<5>::BOXX * 8;
+    const double2 mid = tma::lds2(sm);
+    const double l = tma::lds1(sm - 8);
+    const double r = tma::lds1(sm + 16);
+    const double2 u = tma::lds2(sm - ROW);
+    const double2 d = tma::lds2(sm + ROW);
+    const double2 below = tma::lds2(sb);
+    const double2 above = tma::lds2(sa);
+    s0 = ((((l + mid.y) + u.x) + d.x) + below.x) + above.x;
+    s1 = ((((mid.x + r) + u.y) + d.y) + below.y) + above.y;
+    v0 = fast_third(s0) - p.x;
+    v1 = fast_third(s1) - p.y;
+}
+__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 2)
+wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__ Bp, double* __restrict__ Cp,
+           double* __restrict__ Dp, const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y,
+           int zchunks, int* __restrict__ flag) {
+    constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
+    constexpr int K1 = Cfg::L1_PER_THREAD;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (tma::smem_u32(smem_raw) + 127u) & ~127u;  // level-0 ring
+    const uint32_t l1base = base + NS * Cfg::STAGE_BYTES;            // level-1 ring (3 planes)
+    const uint32_t bars = l1base + 3 * Cfg::STAGE_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma::prefetch_map(&a_map);
+        for (int s = 0; s < NS; ++s) tma::mbar_init(bars + 8 * s, 1);
+        tma::fence_barrier_init();
+        tma::fence_proxy_async();
+    }
+    const unsigned item = blockIdx.x;
+    const int tile_x = (int)(item % (unsigned)tiles_x);
+    const int tile_y = (int)((item / (unsigned)tiles_x) % (unsigned)tiles_y);
+    const int chunk = (int)(item / ((unsigned)tiles_x * (unsigned)tiles_y));
+    const int x0 = tile_x * TX, y0 = tile_y * TY;
+    const int zs = 1 + (int)(((long long)g.nzl * chunk) / zchunks);
+    const int ze = 1 + (int)(((long long)g.nzl * (chunk + 1)) / zchunks);
+    // level-0 planes zs-2 .. ze+1 are streamed; box origin: column WG_XO + x0 - 2, padded row y0 - 1
+    const int n_planes = ze - zs + 4;
+    const int bx = WG_XO + x0 - 2, by = y0 - 1;
+    const uint32_t sp = (uint32_t)g.plane, ksp = (uint32_t)g.cplane;
+    __syncthreads();
+
+    int issued = 0;
+    if (tid == 0) {
+        const int pre = n_planes < NS ? n_planes : NS;
+        for (; issued < pre; ++issued) {
+            tma::mbar_arrive_expect_tx(bars + 8 * issued, Cfg::BOX_BYTES);
+            tma::load_box_3d(base + issued * Cfg::STAGE_BYTES, &a_map, bars + 8 * issued, bx, by, zs - 2 + issued);
+        }
+    }
+
+    // ---- level-1 domain of this thread: pairs j = tid + 256 k of the 66 x 10 inner box ----------
+    uint32_t so1[K1];   // byte offset of the pair inside a stage
+    long long go1[K1];  // element offset inside plane 0 of the padded arrays
+    long long ko1[K1];  // class byte inside plane 0
+    bool in_mesh1[K1], owned1[K1];
+#pragma unroll
+    for (int k = 0; k < K1; ++k) {
+        const int j = tid + Cfg::THREADS * k;
+        const int r = j / (BOXX / 2), c = j % (BOXX / 2);  // r in [0, TY+2), c in [0, 66)
+        const int x = x0 - 2 + 2 * c, y = y0 - 1 + r;
+        const bool live = j < Cfg::L1_PAIRS;
+        so1[k] = (uint32_t)(((r + 1) * BOXX + 2 * c) * 8);
+        go1[k] = (long long)(y + 1) * g.px + WG_XO + x;
+        in_mesh1[k] = live && x >= 0 && x < g.dx && y >= 0 && y < g.dy;
+        ko1[k] = (long long)y * g.pc + (x >> 1);
+        owned1[k] = in_mesh1[k] && c >= 1 && c < BOXX / 2 - 1 && r >= 1 && r < TY + 1;
+        if (!live) so1[k] = 0xffffffffu;
+    }
+    // ---- owned pairs (level 2): the mapping of wg_air_tma, R = 2 rows per thread ------------------
+    const int tx = tid & 63, ty = tid >> 6;
+    const int x = x0 + 2 * tx;
+    const uint32_t so2 = (uint32_t)(((ty + 2) * BOXX + 2 * tx + 2) * 8);
+    bool valid2[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) valid2[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
+    const uint32_t rstep = 4u * (uint32_t)g.px, krstep = 4u * (uint32_t)g.pc;
+
+    int bad = 0;
+    // iteration z: level 1 of plane q = z + 1 (if q >= zs - 1), then level 2 of plane z (if z >= zs).
+    // Level-0 plane p sits in stage (p - (zs - 2)) % NS, level-1 plane q in stage (q + 3) % 3.
+    int st0 = 0;          // stage of level-0 plane z
+    uint32_t ph0 = 0;     // phase bits, one per stage (bit s = parity to wait for next)
+    for (int z = zs - 2; z < ze; ++z) {
+        const int q = z + 1;
+        // the three level-0 planes z, z+1, z+2: wait for z+2 (earlier ones were waited for before),
+        // on the first iteration for all three
+        {
+            const int first = (z == zs - 2) ? 0 : 2;
+            for (int d = first; d < 3; ++d) {
+                int st = st0 + d;
+                if (st >= NS) st -= NS;
+                tma::mbar_wait(bars + 8 * st, (ph0 >> st) & 1u);
+                ph0 ^= 1u << st;
+            }
+        }
+        int sg1 = st0 + 1, sg2 = st0 + 2;
+        if (sg1 >= NS) sg1 -= NS;
+        if (sg2 >= NS) sg2 -= NS;
+        const uint32_t s_lo = base + st0 * Cfg::STAGE_BYTES, s_mid = base + sg1 * Cfg::STAGE_BYTES,
+                       s_hi = base + sg2 * Cfg::STAGE_BYTES;
+        // ---- level 1 of plane q -------------------------------------------------------------------
+        const uint32_t l1_q = l1base + (uint32_t)((q + 3) % 3) * Cfg::STAGE_BYTES;
+        const bool q_real = q >= 1 && q <= g.nzl;       // ghost planes hold no nodes (single GPU): 0
+        const bool q_owned = q >= zs && q < ze;
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+            if (so1[k] == 0xffffffffu) continue;
+            double v0 = 0.0, v1 = 0.0;
+            unsigned ck = CLS_NONE;
+            if (q_real && in_mesh1[k]) {
+                ck = code[(long long)q * ksp + ko1[k]];
+                const double2 p = ld2(Bp + ((long long)q * sp + go1[k]));
+                double s0, s1;
+                tb2_pair(s_lo + so1[k], s_mid + so1[k], s_hi + so1[k], p, v0, v1, s0, s1);
+                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
+                if (!(c0 & 1u)) v0 = 0.0;  // AIR = 1, SHELL = 3: odd
+                if (!(c1 & 1u)) v1 = 0.0;
+                if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
+                    if (c0 & 1u) v0 = slow_third(s0) - p.x;
+                    if (c1 & 1u) v1 = slow_third(s1) - p.y;
+                    if (q_owned && owned1[k]) bad |= classify_bad(v0) | classify_bad(v1);
+                }
+            }
+            sts2(l1_q + so1[k], make_double2(v0, v1));
+            if (q_owned && owned1[k]) {  // p(n+1) of the nodes this CTA owns (boundary nodes: their kernel)
+                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
+                double* dst = Cp + ((long long)q * sp + go1[k]);
+                if (c0 != CLS_BOUNDARY && c1 != CLS_BOUNDARY) st2(dst, make_double2(v0, v1));
+                else {
+                    if (c0 != CLS_BOUNDARY) dst[0] = v0;
+                    if (c1 != CLS_BOUNDARY) dst[1] = v1;
+                }
+            }
+        }
+        __syncthreads();  // level-1 plane q complete
+        // ---- level 2 of plane z ----------------------------------------------------------------------
+        if (z >= zs) {
+            const uint32_t l1_b = l1base + (uint32_t)((z + 2) % 3) * Cfg::STAGE_BYTES;  // plane z - 1
+            const uint32_t l1_m = l1base + (uint32_t)((z + 3) % 3) * Cfg::STAGE_BYTES;  // plane z
+            const uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, z);
+            const uint32_t koff = (uint32_t)(((long long)z * g.dy + y0 + ty) * g.pc + (x >> 1));
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (!valid2[rr]) continue;
+                const uint32_t o = so2 + rr * (4 * BOXX * 8);
+                const unsigned ck = code[koff + rr * krstep];
+                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
+                const double2 p = tma::lds2(s_lo + o);  // p(n) of the pair: level-0 plane z
+                double v0, v1, s0, s1;
+                tb2_pair(l1_b + o, l1_m + o, l1_q + o, p, v0, v1, s0, s1);
+                if (c0 != CLS_AIR) v0 = 0.0;
+                if (c1 != CLS_AIR) v1 = 0.0;
+                if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
+                    if (c0 == CLS_AIR) v0 = slow_third(s0) - p.x;
+                    if (c1 == CLS_AIR) v1 = slow_third(s1) - p.y;
+                    bad |= classify_bad(v0) | classify_bad(v1);
+                }
+                // AIR: the value; NONE: 0; SHELL and BOUNDARY: other kernels
+                const bool w0 = c0 == CLS_AIR || c0 == CLS_NONE, w1 = c1 == CLS_AIR || c1 == CLS_NONE;
+                double* dst = Dp + (off + rr * rstep);
+                if (w0 && w1) st2(dst, make_double2(v0, v1));
+                else {
+                    if (w0) dst[0] = v0;
+                    if (w1) dst[1] = v1;
+                }
+            }
+        }
+        __syncthreads();  // level-0 plane z and level-1 plane z - 1 are free
+        if (tid == 0 && issued < n_planes) {
+            tma::mbar_arrive_expect_tx(bars + 8 * st0, Cfg::BOX_BYTES);
+            tma::load_box_3d(base + st0 * Cfg::STAGE_BYTES, &a_map, bars + 8 * st0, bx, by, zs - 2 + issued);
+            ++issued;
+        }
+        st0 = sg1;
+    }
+    raise_flags(bad, flag);
+}
+
+// p(n+2) of the shell nodes (AIR with a boundary neighbour): the same update as update_pair for one
+// node, gathered from the finished p(n+1) array. One thread per list entry (sorted by offset).
+__global__ void __launch_bounds__(256)
+wg_shell(const double* __restrict__ Cp, const double* __restrict__ Ap, double* __restrict__ Dp,
+         const uint32_t* __restrict__ offs, uint32_t n, WgGeom g, int* __restrict__ flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (t < n) {
+        const uint32_t off = offs[t];
+        const double* c = Cp + off;
+        const double s = ((((c[-1] + c[1]) + c[-(long long)g.px]) + c[g.px]) + c[-g.plane]) + c[g.plane];
+        const double p = Ap[off];
+        double v = fast_third(s) - p;
+        if (abs_hi(v) >= 0x7ff00000u) {
+            v = slow_third(s) - p;
+            bad = classify_bad(v);
+        }
+        Dp[off] = v;
+    }
+    raise_flags(bad, flag);
+}
+
+// ---------------------------------------------------------------------------
 // Boundary nodes: boundary_N (program.cpp:331-387) and everything it calls.
 // One thread per list entry; filter state is SoA so consecutive threads touch
 // consecutive doubles.
@@ -493,7 +741,7 @@ __device__ __forceinline__ void filter_step_6(double input, double (&m)[6],
 
 template <int N>
 __device__ __forceinline__ int boundary_node(const double* __restrict__ cur,
-                                             double* __restrict__ prev, const BList& L, uint32_t t,
+                                             double* __restrict__ prev, double* out, const BList& L, uint32_t t,
                                              const wvb_coefficients_canonical* __restrict__ coeffs,
                                              const WgGeom& g, double courant, double courant_sq) {
     int bad = 0;
@@ -578,7 +826,7 @@ __device__ __forceinline__ int boundary_node(const double* __restrict__ cur,
             for (int k = 0; k < 6; ++k) L.mem[((size_t)i * 6 + k) * L.n + t] = mem[i][k];
         }
         bad |= classify_bad(ret);
-        prev[off] = ret;
+        out[off] = ret;
     }
     return bad;
 }
@@ -674,7 +922,7 @@ __device__ __forceinline__ B1Data b1_load_data(const double* __restrict__ cur,
     for (int k = 0; k < 6; ++k) d.m[k] = L.mem[(size_t)k * L.n + t];
     return d;
 }
-__device__ __forceinline__ int b1_compute(double* __restrict__ prev, const BList& L, uint32_t t,
+__device__ __forceinline__ int b1_compute(double* out, const BList& L, uint32_t t,
                                           const B1Entry& e, B1Data& d,
                                           const wvb_coefficients_canonical* __restrict__ coeffs,
                                           double courant, double courant_sq) {
@@ -700,11 +948,11 @@ __device__ __forceinline__ int b1_compute(double* __restrict__ prev, const BList
 #pragma unroll
     for (int k = 0; k < 6; ++k) L.mem[(size_t)k * L.n + t] = d.m[k];
     bad |= classify_bad(ret);
-    prev[e.off] = ret;
+    out[e.off] = ret;
     return bad;
 }
 __device__ __forceinline__ int boundary_1d_pipelined(
-        const double* __restrict__ cur, double* __restrict__ prev, const BList& L, uint32_t t,
+        const double* __restrict__ cur, double* __restrict__ prev, double* out, const BList& L, uint32_t t,
         uint32_t stride, const wvb_coefficients_canonical* __restrict__ coeffs, const WgGeom& g,
         double courant, double courant_sq) {
     int bad = 0;
@@ -718,7 +966,7 @@ __device__ __forceinline__ int boundary_1d_pipelined(
         B1Entry e2 = e1;
         if (more) d1 = b1_load_data(cur, prev, L, t1, e1, g);
         if (t2 < L.n) e2 = b1_load_entry(L, t2);
-        bad |= b1_compute(prev, L, t, e0, d0, coeffs, courant, courant_sq);
+        bad |= b1_compute(out, L, t, e0, d0, coeffs, courant, courant_sq);
         if (!more) break;
         e0 = e1;
         d0 = d1;
@@ -732,28 +980,31 @@ __device__ __forceinline__ int boundary_1d_pipelined(
 // [nb1, nb1 + nb2) the 2-d list, the rest the 3-d list. Runs on its own stream
 // next to the air-node kernel: the two touch disjoint nodes of `prev` and only
 // read `cur`.
-template <int THREADS, int MINB, bool PIPE>
+// SEP = false: the result replaces `previous` in place (the step as the reference does it);
+// SEP = true (temporal blocking): previous is only read, the result goes to out_sep.
+template <int THREADS, int MINB, bool PIPE, bool SEP = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 wg_boundary_all(const double* __restrict__ cur, double* __restrict__ prev, BList L1, BList L2,
                 BList L3, uint32_t nb1, uint32_t nb2,
                 const wvb_coefficients_canonical* __restrict__ coeffs, WgGeom g, double courant,
-                double courant_sq, int* __restrict__ flag) {
+                double courant_sq, int* __restrict__ flag, double* out_sep) {
     int bad = 0;
+    double* const out = SEP ? out_sep : prev;
     const uint32_t b = blockIdx.x;
     if (b < nb1) {
         const uint32_t t = b * THREADS + threadIdx.x;
         if (PIPE) {  // nb1 blocks stride over the whole list
-            bad = boundary_1d_pipelined(cur, prev, L1, t, nb1 * THREADS, coeffs, g, courant,
+            bad = boundary_1d_pipelined(cur, prev, out, L1, t, nb1 * THREADS, coeffs, g, courant,
                                         courant_sq);
         } else if (t < L1.n) {
-            bad = boundary_node<1>(cur, prev, L1, t, coeffs, g, courant, courant_sq);
+            bad = boundary_node<1>(cur, prev, out, L1, t, coeffs, g, courant, courant_sq);
         }
     } else if (b < nb1 + nb2) {
         const uint32_t t = (b - nb1) * THREADS + threadIdx.x;
-        if (t < L2.n) bad = boundary_node<2>(cur, prev, L2, t, coeffs, g, courant, courant_sq);
+        if (t < L2.n) bad = boundary_node<2>(cur, prev, out, L2, t, coeffs, g, courant, courant_sq);
     } else {
         const uint32_t t = (b - nb1 - nb2) * THREADS + threadIdx.x;
-        if (t < L3.n) bad = boundary_node<3>(cur, prev, L3, t, coeffs, g, courant, courant_sq);
+        if (t < L3.n) bad = boundary_node<3>(cur, prev, out, L3, t, coeffs, g, courant, courant_sq);
     }
     raise_flags(bad, flag);
 }
