@@ -458,9 +458,10 @@ def test_temporal_blocking_l_shaped_room_and_random_field():
         for n in (1, 2, 3):
             assert_parity(g.boundary_data(n)["filter_memory"].ravel(), o.boundary_data(n)["mem"].ravel())
     # error flags survive the fusion: an inf planted next to a wall is reported like the reference does
+    # (wvb_wg_step ORs the flags of the steps of one call; the oracle reports step by step)
     o2 = wgo.Sim(om)
     o2.write(om.index(30, 8, 7), np.inf)
-    fo = o2.step(4)
+    fo = o2.step(1) | o2.step(1)
     with wvb.Waveguide(to_wvb(om), kernel=_lib.KERNEL_TMA, flags=_lib.TEMPORAL2) as g:
         g.write(om.index(30, 8, 7), np.inf)
-        assert g.step(4) == fo and fo != 0
+        assert g.step(2) == fo and fo != 0

@@ -35,6 +35,10 @@ void set_last_error(const char* fmt, ...) {
     g_last_error = buf;
 }
 
+#ifndef WVB_TB2_THREADS
+#define WVB_TB2_THREADS 512
+#endif
+
 namespace {
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -535,7 +539,7 @@ void enqueue_step(wvb_wg* w) {
 // Afterwards D is `current` and C `previous`: the handle's two arrays trade places with the two
 // scratch arrays (pointers and tensor maps), so everything else keeps addressing P[cur].
 void enqueue_pair(wvb_wg* w) {
-    using Cfg = Tb2Cfg<5>;
+    using Cfg = Tb2Cfg<5, WVB_TB2_THREADS>;
     auto& tb = w->tb;
     const int ci = w->cur, pi = w->cur ^ 1;
     double* A = w->P[ci].p;
@@ -920,7 +924,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     if ((d->flags & WVB_WG_TEMPORAL2) || env_int("WVB_WG_TB2", 0)) {
         WVB_REQUIRE(d->nranks == 1 && tma_fits, WVB_ERR_UNSUPPORTED,
                     "WVB_WG_TEMPORAL2 needs a single-GPU handle and a mesh of at least 132 x 10 nodes per plane");
-        using Cfg = Tb2Cfg<5>;
+        using Cfg = Tb2Cfg<5, WVB_TB2_THREADS>;
         auto& tb = w->tb;
         // class map with SHELL = an AIR node with a BOUNDARY node among its six neighbours
         auto cls_at = [&](int x, int y, int lz) -> int {

@@ -483,24 +483,27 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
 // ---------------------------------------------------------------------------
 enum : uint8_t { CLS_SHELL = 3 };  // TB2's class map only: AIR with a BOUNDARY neighbour
 
-template <int NSTAGE_>
+template <int NSTAGE_, int THREADS_>
 struct Tb2Cfg {
     static constexpr int TX = 128, TY = 8;
     static constexpr int NSTAGE = NSTAGE_;       // level-0 ring: 3 live planes + prefetch
     static constexpr int BOXX = TX + 4, BOXY = TY + 4;
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = THREADS_;
     static constexpr int L1_PAIRS = (BOXX / 2) * (TY + 2);          // 66 x 10 = 660
-    static constexpr int L1_PER_THREAD = (L1_PAIRS + THREADS - 1) / THREADS;  // 3
+    static constexpr int L1_PER_THREAD = (L1_PAIRS + THREADS - 1) / THREADS;
+    static constexpr int ROW_GROUPS = THREADS / 64;                  // owned rows handled side by side
+    static constexpr int L2_PER_THREAD = TY / ROW_GROUPS;
     static constexpr uint32_t BOX_BYTES = BOXX * BOXY * 8;           // 12 672
     static constexpr uint32_t STAGE_BYTES = (BOX_BYTES + 127u) & ~127u;
     static constexpr uint32_t SMEM_BYTES = (NSTAGE + 3) * STAGE_BYTES + NSTAGE * 8 + 128;
     static_assert(NSTAGE >= 4, "three live level-0 planes + at least one in flight");
+    static_assert(THREADS % 64 == 0 && TY % ROW_GROUPS == 0, "thread count must tile the rows");
 };
 
 // one pair of nodes: v = third(sum of six ports) - p, the arithmetic of update_pair
 __device__ __forceinline__ void tb2_pair(uint32_t sb, uint32_t sm, uint32_t sa, double2 p, double& v0,
                                          double& v1, double& s0, double& s1) {
-    constexpr uint32_t ROW = Tb2Cfg<5>::BOXX * 8;
+    constexpr uint32_t ROW = (128 + 4) * 8;
     const double2 mid = tma::lds2(sm);
     const double l = tma::lds1(sm - 8);
     const double r = tma::lds1(sm + 16);
@@ -516,6 +519,13 @@ __device__ __forceinline__ void tb2_pair(uint32_t sb, uint32_t sm, uint32_t sa, 
 __device__ __forceinline__ void sts2(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
+__device__ __forceinline__ void store_unless_boundary(double* dst, double v0, double v1, bool w0, bool w1) {
+    if (w0 && w1) st2(dst, make_double2(v0, v1));
+    else {
+        if (w0) dst[0] = v0;
+        if (w1) dst[1] = v1;
+    }
+}
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 2)
@@ -523,7 +533,7 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
            double* __restrict__ Dp, const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y,
            int zchunks, int* __restrict__ flag) {
     constexpr int TX = Cfg::TX, TY = Cfg::TY, NS = Cfg::NSTAGE, BOXX = Cfg::BOXX;
-    constexpr int K1 = Cfg::L1_PER_THREAD;
+    constexpr int K1 = Cfg::L1_PER_THREAD, K2 = Cfg::L2_PER_THREAD, RG = Cfg::ROW_GROUPS;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 127u) & ~127u;  // level-0 ring
     const uint32_t l1base = base + NS * Cfg::STAGE_BYTES;            // level-1 ring (3 planes)
@@ -557,40 +567,79 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
         }
     }
 
-    // ---- level-1 domain of this thread: pairs j = tid + 256 k of the 66 x 10 inner box ----------
-    uint32_t so1[K1];   // byte offset of the pair inside a stage
-    long long go1[K1];  // element offset inside plane 0 of the padded arrays
-    long long ko1[K1];  // class byte inside plane 0
-    bool in_mesh1[K1], owned1[K1];
+    // ---- level-1 domain of this thread: pairs j = tid + THREADS k of the 66 x 10 inner box -------
+    // flags: bit 0 = the slot exists, bit 1 = inside the mesh, bit 2 = owned by this CTA
+    uint32_t so1[K1], go1[K1], ko1[K1], fl1[K1];  // smem byte offset / element and class-byte offset in plane q
 #pragma unroll
     for (int k = 0; k < K1; ++k) {
         const int j = tid + Cfg::THREADS * k;
         const int r = j / (BOXX / 2), c = j % (BOXX / 2);  // r in [0, TY+2), c in [0, 66)
         const int x = x0 - 2 + 2 * c, y = y0 - 1 + r;
         const bool live = j < Cfg::L1_PAIRS;
+        const bool in_mesh = live && x >= 0 && x < g.dx && y >= 0 && y < g.dy;
+        const bool owned = in_mesh && c >= 1 && c < BOXX / 2 - 1 && r >= 1 && r < TY + 1;
         so1[k] = (uint32_t)(((r + 1) * BOXX + 2 * c) * 8);
-        go1[k] = (long long)(y + 1) * g.px + WG_XO + x;
-        in_mesh1[k] = live && x >= 0 && x < g.dx && y >= 0 && y < g.dy;
-        ko1[k] = (long long)y * g.pc + (x >> 1);
-        owned1[k] = in_mesh1[k] && c >= 1 && c < BOXX / 2 - 1 && r >= 1 && r < TY + 1;
-        if (!live) so1[k] = 0xffffffffu;
+        fl1[k] = (live ? 1u : 0u) | (in_mesh ? 2u : 0u) | (owned ? 4u : 0u);
+        // offsets for plane zs - 1 (the first level-1 plane); clamped to something valid when unused
+        go1[k] = in_mesh ? (uint32_t)((long long)(zs - 1) * g.plane + (long long)(y + 1) * g.px + WG_XO + x) : 0u;
+        ko1[k] = in_mesh ? (uint32_t)((long long)(zs - 1) * g.cplane + (long long)y * g.pc + (x >> 1)) : 0u;
     }
-    // ---- owned pairs (level 2): the mapping of wg_air_tma, R = 2 rows per thread ------------------
+    // ---- owned pairs (level 2): pair column tx, rows ty + RG rr ------------------------------------
     const int tx = tid & 63, ty = tid >> 6;
     const int x = x0 + 2 * tx;
     const uint32_t so2 = (uint32_t)(((ty + 2) * BOXX + 2 * tx + 2) * 8);
-    bool valid2[2];
+    bool valid2[K2];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) valid2[rr] = (x < g.dx) && (y0 + ty + 4 * rr < g.dy);
-    const uint32_t rstep = 4u * (uint32_t)g.px, krstep = 4u * (uint32_t)g.pc;
+    for (int rr = 0; rr < K2; ++rr) valid2[rr] = (x < g.dx) && (y0 + ty + RG * rr < g.dy);
+    const uint32_t rstep = (uint32_t)RG * (uint32_t)g.px, krstep = (uint32_t)RG * (uint32_t)g.pc;
+    uint32_t off2 = (uint32_t)wg_offset(g, x, y0 + ty, zs);                                       // plane zs
+    uint32_t koff2 = (uint32_t)(((long long)zs * g.dy + y0 + ty) * g.pc + (x >> 1));
 
     int bad = 0;
-    // iteration z: level 1 of plane q = z + 1 (if q >= zs - 1), then level 2 of plane z (if z >= zs).
+    // Operands that come straight from global memory (p(n-1) and the class bytes) are fetched one
+    // iteration ahead, like wg_air_tma does, so their latency hides under the previous plane.
+    double2 pB_next[K1];
+    unsigned c1_next[K1], c2_next[K2];
+    auto fetch_level1 = [&](int q) {  // operands of level 1 of plane q (go1 / ko1 point at plane q)
+        const bool q_real = q >= 1 && q <= g.nzl;  // ghost planes hold no nodes (single GPU): 0
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+            pB_next[k] = make_double2(0.0, 0.0);
+            c1_next[k] = CLS_NONE;
+            if (q_real && (fl1[k] & 2u)) {
+                c1_next[k] = code[ko1[k]];
+                pB_next[k] = ld2(Bp + go1[k]);
+            }
+        }
+    };
+    auto fetch_level2 = [&](uint32_t koff) {  // classes of the owned pairs of a plane
+#pragma unroll
+        for (int rr = 0; rr < K2; ++rr)
+            c2_next[rr] = valid2[rr] ? code[koff + rr * krstep] : (unsigned)(CLS_BOUNDARY | (CLS_BOUNDARY << 4));
+    };
+    fetch_level1(zs - 1);
+    fetch_level2(koff2);
+    // iteration z: level 1 of plane q = z + 1, then level 2 of plane z (if z >= zs).
     // Level-0 plane p sits in stage (p - (zs - 2)) % NS, level-1 plane q in stage (q + 3) % 3.
     int st0 = 0;          // stage of level-0 plane z
     uint32_t ph0 = 0;     // phase bits, one per stage (bit s = parity to wait for next)
     for (int z = zs - 2; z < ze; ++z) {
         const int q = z + 1;
+        double2 pB[K1];
+        unsigned c1[K1], c2[K2];
+        uint32_t gq[K1];
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+            pB[k] = pB_next[k];
+            c1[k] = c1_next[k];
+            gq[k] = go1[k];  // element offset of the pair in plane q
+            go1[k] += sp;
+            ko1[k] += ksp;
+        }
+#pragma unroll
+        for (int rr = 0; rr < K2; ++rr) c2[rr] = c2_next[rr];
+        if (q < ze) fetch_level1(q + 1);
+        if (z >= zs && z + 1 < ze) fetch_level2(koff2 + ksp);
         // the three level-0 planes z, z+1, z+2: wait for z+2 (earlier ones were waited for before),
         // on the first iteration for all three
         {
@@ -609,70 +658,60 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
                        s_hi = base + sg2 * Cfg::STAGE_BYTES;
         // ---- level 1 of plane q -------------------------------------------------------------------
         const uint32_t l1_q = l1base + (uint32_t)((q + 3) % 3) * Cfg::STAGE_BYTES;
-        const bool q_real = q >= 1 && q <= g.nzl;       // ghost planes hold no nodes (single GPU): 0
         const bool q_owned = q >= zs && q < ze;
 #pragma unroll
         for (int k = 0; k < K1; ++k) {
-            if (so1[k] == 0xffffffffu) continue;
+            if (!(fl1[k] & 1u)) continue;
+            const unsigned ck = c1[k];
+            const unsigned c0 = ck & 0xfu, c1b = ck >> 4;
+            const bool mine = q_owned && (fl1[k] & 4u);
             double v0 = 0.0, v1 = 0.0;
-            unsigned ck = CLS_NONE;
-            if (q_real && in_mesh1[k]) {
-                ck = code[(long long)q * ksp + ko1[k]];
-                const double2 p = ld2(Bp + ((long long)q * sp + go1[k]));
+            if ((c0 | c1b) & 1u) {  // AIR = 1, SHELL = 3: odd
+                const double2 p = pB[k];
                 double s0, s1;
                 tb2_pair(s_lo + so1[k], s_mid + so1[k], s_hi + so1[k], p, v0, v1, s0, s1);
-                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
-                if (!(c0 & 1u)) v0 = 0.0;  // AIR = 1, SHELL = 3: odd
-                if (!(c1 & 1u)) v1 = 0.0;
+                if (!(c0 & 1u)) v0 = 0.0;
+                if (!(c1b & 1u)) v1 = 0.0;
                 if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
                     if (c0 & 1u) v0 = slow_third(s0) - p.x;
-                    if (c1 & 1u) v1 = slow_third(s1) - p.y;
-                    if (q_owned && owned1[k]) bad |= classify_bad(v0) | classify_bad(v1);
+                    if (c1b & 1u) v1 = slow_third(s1) - p.y;
+                    if (mine) bad |= classify_bad(v0) | classify_bad(v1);
                 }
             }
             sts2(l1_q + so1[k], make_double2(v0, v1));
-            if (q_owned && owned1[k]) {  // p(n+1) of the nodes this CTA owns (boundary nodes: their kernel)
-                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
-                double* dst = Cp + ((long long)q * sp + go1[k]);
-                if (c0 != CLS_BOUNDARY && c1 != CLS_BOUNDARY) st2(dst, make_double2(v0, v1));
-                else {
-                    if (c0 != CLS_BOUNDARY) dst[0] = v0;
-                    if (c1 != CLS_BOUNDARY) dst[1] = v1;
-                }
-            }
+            // p(n+1) of the nodes this CTA owns (boundary nodes: their kernel)
+            if (mine) store_unless_boundary(Cp + gq[k], v0, v1, c0 != CLS_BOUNDARY, c1b != CLS_BOUNDARY);
         }
         __syncthreads();  // level-1 plane q complete
         // ---- level 2 of plane z ----------------------------------------------------------------------
         if (z >= zs) {
             const uint32_t l1_b = l1base + (uint32_t)((z + 2) % 3) * Cfg::STAGE_BYTES;  // plane z - 1
             const uint32_t l1_m = l1base + (uint32_t)((z + 3) % 3) * Cfg::STAGE_BYTES;  // plane z
-            const uint32_t off = (uint32_t)wg_offset(g, x, y0 + ty, z);
-            const uint32_t koff = (uint32_t)(((long long)z * g.dy + y0 + ty) * g.pc + (x >> 1));
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
+            for (int rr = 0; rr < K2; ++rr) {
                 if (!valid2[rr]) continue;
-                const uint32_t o = so2 + rr * (4 * BOXX * 8);
-                const unsigned ck = code[koff + rr * krstep];
-                const unsigned c0 = ck & 0xfu, c1 = ck >> 4;
-                const double2 p = tma::lds2(s_lo + o);  // p(n) of the pair: level-0 plane z
-                double v0, v1, s0, s1;
-                tb2_pair(l1_b + o, l1_m + o, l1_q + o, p, v0, v1, s0, s1);
-                if (c0 != CLS_AIR) v0 = 0.0;
-                if (c1 != CLS_AIR) v1 = 0.0;
-                if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
-                    if (c0 == CLS_AIR) v0 = slow_third(s0) - p.x;
-                    if (c1 == CLS_AIR) v1 = slow_third(s1) - p.y;
-                    bad |= classify_bad(v0) | classify_bad(v1);
+                const uint32_t o = so2 + rr * (RG * BOXX * 8);
+                const unsigned ck = c2[rr];
+                const unsigned c0 = ck & 0xfu, c1b = ck >> 4;
+                const bool w0 = c0 == CLS_AIR || c0 == CLS_NONE, w1 = c1b == CLS_AIR || c1b == CLS_NONE;
+                if (!(w0 || w1)) continue;  // SHELL and BOUNDARY: other kernels
+                double v0 = 0.0, v1 = 0.0;
+                if (c0 == CLS_AIR || c1b == CLS_AIR) {
+                    const double2 p = tma::lds2(s_lo + o);  // p(n) of the pair: level-0 plane z
+                    double s0, s1;
+                    tb2_pair(l1_b + o, l1_m + o, l1_q + o, p, v0, v1, s0, s1);
+                    if (c0 != CLS_AIR) v0 = 0.0;
+                    if (c1b != CLS_AIR) v1 = 0.0;
+                    if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
+                        if (c0 == CLS_AIR) v0 = slow_third(s0) - p.x;
+                        if (c1b == CLS_AIR) v1 = slow_third(s1) - p.y;
+                        bad |= classify_bad(v0) | classify_bad(v1);
+                    }
                 }
-                // AIR: the value; NONE: 0; SHELL and BOUNDARY: other kernels
-                const bool w0 = c0 == CLS_AIR || c0 == CLS_NONE, w1 = c1 == CLS_AIR || c1 == CLS_NONE;
-                double* dst = Dp + (off + rr * rstep);
-                if (w0 && w1) st2(dst, make_double2(v0, v1));
-                else {
-                    if (w0) dst[0] = v0;
-                    if (w1) dst[1] = v1;
-                }
+                store_unless_boundary(Dp + (off2 + rr * rstep), v0, v1, w0, w1);
             }
+            off2 += sp;
+            koff2 += ksp;
         }
         __syncthreads();  // level-0 plane z and level-1 plane z - 1 are free
         if (tid == 0 && issued < n_planes) {
