@@ -330,6 +330,11 @@ void wvb_rt_destroy(wvb_rt* rt);
  * (n_bins, directional) until wvb_rt_reset_histogram(); layout [n_bins][8]
  * doubles, or [20][9][n_bins][8] when directional (vector_look_up_table<..,20,9>).
  * Impulses at or beyond n_bins are counted in *dropped. */
+enum {
+    WVB_RT_MODE_AUTO = 0,      /* by batch size                                                        */
+    WVB_RT_MODE_RAY_LIFE = 1,  /* one thread per ray for all its reflections, one launch                */
+    WVB_RT_MODE_WAVEFRONT = 2  /* one launch per reflection, rays re-binned by (voxel, direction) between */
+};
 typedef struct {
     float source[3];
     float receiver[3];
@@ -345,7 +350,7 @@ typedef struct {
     uint32_t n_bins;
     uint32_t directional;
     uint32_t keep_steps; /* reflections of steps < keep_steps are returned (image-source / visual consumers) */
-    uint32_t pad1_;
+    uint32_t mode;       /* WVB_RT_MODE_*: how the loop is scheduled on the device; results are the same */
 } wvb_rt_trace_params;
 
 /* directions: n_rays x 3 floats on the host (the iterator range raytracer::run

@@ -22,7 +22,7 @@ class TraceParams(C.Structure):
         ("speed_of_sound", C.c_double), ("histogram_rate", C.c_double),
         ("total_rays", C.c_uint64), ("seed", C.c_uint64), ("ray_index_base", C.c_uint64),
         ("depth", C.c_uint32), ("specular_from_step", C.c_uint32), ("n_bins", C.c_uint32),
-        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("pad1", C.c_uint32),
+        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("pad1", C.c_uint32),  # pad1: the product's scheduling mode, unused here
     ]
 
 

@@ -150,3 +150,69 @@ def test_config5_sized_run_statistics():
     small_diffuse, _, _ = o.trace(dirs, src, rcv, depth, seed=77, specular_from_step=depth)
     assert np.abs(big.sum(0) / small.sum(0) - 1).max() < 0.10
     assert np.abs(big_diffuse.sum(0) / small_diffuse.sum(0) - 1).max() < 0.02
+
+
+# ---- the wavefront schedule (one launch per reflection, rays re-binned in between) ------------------
+from wayverb_b200 import _lib  # noqa: E402
+
+
+@pytest.mark.parametrize("scatter,per_wall", [(0.0, False), (0.1, True), (0.6, False)])
+def test_wavefront_schedule_matches_oracle_and_ray_life(scatter, per_wall):
+    sc = room(scatter, subdiv=3, side=8, per_wall=per_wall)
+    o = rto.Scene(sc)
+    n, depth, keep = 30000, 40, 8
+    d = rto.directions(99, n)
+    want_h, want_r, want_drop = o.trace(d, SRC, RCV, depth, seed=5, specular_from_step=2, keep_steps=keep)
+    with wvb.RayTracer(sc) as g:
+        refl, dropped, ms = g.trace(d, SRC, RCV, depth, seed=5, specular_from_step=2, keep_steps=keep,
+                                    mode=_lib.RT_MODE_WAVEFRONT)
+        got_h = g.histogram()
+        g.reset_histogram()
+        refl1, _, _ = g.trace(d, SRC, RCV, depth, seed=5, specular_from_step=2, keep_steps=keep,
+                              mode=_lib.RT_MODE_RAY_LIFE)
+        one_h = g.histogram()
+    assert dropped == want_drop == 0 and ms > 0
+    assert np.array_equal(refl.view(np.uint8), want_r.view(np.uint8))      # every byte of every record
+    assert np.array_equal(refl.view(np.uint8), refl1.view(np.uint8))
+    assert_hist_close(got_h, want_h)
+    assert_hist_close(got_h, one_h)
+
+
+def test_wavefront_dead_rays_directional_and_segments():
+    # an open box: rays escape and die at different steps; directional histogram; two segments
+    sc = room(0.2, subdiv=1, side=4)
+    keep = np.ones(sc.triangles.size, bool)
+    keep[:2] = False
+    open_sc = scene.Scene(sc.vertices[:, :3], sc.triangles[keep], sc.surfaces, side=4)
+    n, depth = 40000, 14
+    d = rto.directions(8, n)
+    want_h, want_r, _ = rto.Scene(open_sc).trace(d, SRC, RCV, depth, keep_steps=depth, directional=True, seed=8)
+    with wvb.RayTracer(open_sc) as g:
+        bins = want_h.shape[2]
+        a, _, _ = g.trace(d[:25000], SRC, RCV, depth, total_rays=n, keep_steps=depth, directional=True, seed=8,
+                          n_bins=bins, mode=_lib.RT_MODE_WAVEFRONT)
+        b, _, _ = g.trace(d[25000:], SRC, RCV, depth, total_rays=n, ray_index_base=25000, keep_steps=depth,
+                          directional=True, seed=8, n_bins=bins, mode=_lib.RT_MODE_WAVEFRONT)
+        got_h = g.histogram()
+    got_r = np.concatenate([a, b], 1)
+    assert (want_r["keep_going"] == 0).any() and (want_r["keep_going"] == 1).any()
+    assert np.array_equal(got_r.view(np.uint8), want_r.view(np.uint8))
+    assert_hist_close(got_h.sum((0, 1)), want_h.sum((0, 1)))
+    assert np.abs(got_h - want_h).sum() / want_h.sum() < 1e-3
+
+
+def test_wavefront_on_the_concert_hall_with_image_sources():
+    sc, meta = scene.concert_hall()
+    src, rcv = meta["source"], meta["receiver"]
+    depth, order, n = wvb.reflection_depth(meta["min_absorption"]), 4, 70000   # above the automatic threshold
+    o = rto.Scene(sc)
+    d = rto.directions(0x5eed, n)
+    want_h, want_r, _ = o.trace(d, src, rcv, depth, seed=0x5eed, specular_from_step=order + 1, keep_steps=order)
+    want_i, _ = rto.image_source(o, rto.path_elements(want_r, order), src, rcv)
+    with wvb.RayTracer(sc) as g, wvb.ImageSource(g, src, rcv, max_elements=n * order) as s:
+        got_r = s.trace(d, depth=depth, order=order, seed=0x5eed, specular_from_step=order + 1, keep_steps=order)
+        got_h = g.histogram()
+        got_i, _, _ = s.results()
+    assert np.array_equal(got_r.view(np.uint8), want_r.view(np.uint8))
+    assert np.abs(got_h - want_h).max() <= 1e-9 * np.abs(want_h).max()
+    assert np.array_equal(got_i.view(np.uint8), want_i.view(np.uint8))

@@ -18,9 +18,10 @@ else:                   # BASELINE config 5's geometry: "hall" (322 triangles) o
     src, rcv, depth = meta["source"], meta["receiver"], wvb.reflection_depth(meta["min_absorption"])
 with wvb.RayTracer(sc) as g, wvb.ImageSource(g, src, rcv, max_elements=rays * 4) as s:
     g.trace(None, src, rcv, depth, n_rays=1 << 12, seed=1)
-    g.reset_histogram()
-    _, dropped, ms = g.trace(None, src, rcv, depth, n_rays=rays, seed=2)
-    print(which, rays, depth, ms, rays * depth / ms / 1e3, "ray-reflections/s")
+    for mode, name in ((1, "ray-life"), (2, "wavefront"), (1, "ray-life"), (2, "wavefront")):
+        g.reset_histogram()
+        _, dropped, ms = g.trace(None, src, rcv, depth, n_rays=rays, seed=2, mode=mode)
+        print(which, name, rays, depth, "%.3f ms" % ms, "%.1f M ray-reflections/s" % (rays * depth / ms / 1e3), flush=True)
     s.trace(None, depth=depth, order=4, n_rays=rays, seed=2)
     imp, stats, vms = s.results()
     print("image sources", imp.size, stats.tolist(), vms, "ms validate")

@@ -22,6 +22,7 @@ WVB_OK, WVB_ERR_INVALID, WVB_ERR_CUDA, WVB_ERR_NO_DEVICE, WVB_ERR_NCCL, WVB_ERR_
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 HALO_AUTO, HALO_NCCL, HALO_P2P, HALO_OVERLAP = 0, 1 << 28, 2 << 28, 1 << 30  # wvb_wg_desc.flags
 TEMPORAL2 = 1 << 31
+RT_MODE_AUTO, RT_MODE_RAY_LIFE, RT_MODE_WAVEFRONT = 0, 1, 2  # wvb_rt_trace_params.mode
 
 
 class WgDesc(C.Structure):
@@ -93,7 +94,7 @@ class RtTraceParams(C.Structure):
         ("speed_of_sound", C.c_double), ("histogram_sample_rate", C.c_double),
         ("total_rays", C.c_uint64), ("seed", C.c_uint64), ("ray_index_base", C.c_uint64),
         ("depth", C.c_uint32), ("specular_from_step", C.c_uint32), ("n_bins", C.c_uint32),
-        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("pad1", C.c_uint32),
+        ("directional", C.c_uint32), ("keep_steps", C.c_uint32), ("mode", C.c_uint32),
     ]
 
 

@@ -31,6 +31,9 @@ struct wvb_rt {
     dev_buf<double> hist;
     dev_buf<unsigned long long> dropped;
     dev_buf<float> dirs;
+    // wavefront path (rt_wave): per-ray state and the counting sort's arrays
+    dev_buf<float4> w_pos, w_dir, w_vol;
+    dev_buf<uint32_t> w_alive, w_keys, w_perm, w_bins, w_bsums;
     rt::Scene sc{};
     uint32_t hist_bins = 0, hist_directional = 0;
     float diag = 0;
@@ -88,6 +91,51 @@ cudaStream_t wvb_rt_stream(const wvb_rt* r) { return r->stream; }
 // the histogram's drop counter (impulses beyond n_bins), device resident
 const unsigned long long* wvb_rt_dropped_counter(const wvb_rt* r) { return r->dropped.p; }
 
+// raytracer.h:223-244 as a wavefront: see rt_wave in rt_kernels.cuh
+void trace_wavefront(wvb_rt* r, const rt::Params& P, uint32_t n, rt::ReflectionPod* d_refl) {
+    if (r->w_pos.n < n) {
+        r->w_pos.alloc(n, false);
+        r->w_dir.alloc(n, false);
+        r->w_vol.alloc((size_t)n * 2, false);
+        r->w_alive.alloc(n, false);
+        r->w_keys.alloc(n, false);
+        r->w_perm.alloc(n, false);
+    }
+    uint32_t bits = 0;
+    while ((1u << bits) < r->sc.side) ++bits;
+    rt::WaveState W{};
+    W.key_voxel_shift = bits > 5 ? bits - 5 : 0;
+    W.key_side_bits = bits > 5 ? 5 : std::max(bits, 1u);
+    const uint32_t n_bins = (1u << (3 * W.key_side_bits + 6)) + 1;
+    W.dead_key = n_bins - 1;
+    const uint32_t scan_blocks = (n_bins + 4095) / 4096;
+    if (r->w_bins.n < n_bins) {
+        r->w_bins.alloc(n_bins, false);
+        r->w_bsums.alloc(scan_blocks, false);
+    }
+    W.pos = r->w_pos.p; W.dir = r->w_dir.p; W.vol = r->w_vol.p; W.alive = r->w_alive.p;
+    W.keys = r->w_keys.p; W.perm = r->w_perm.p; W.bins = r->w_bins.p;
+    cudaStream_t st = r->stream;
+    const unsigned blocks = (n + 127) / 128;
+    auto sort = [&] {  // bins hold the key counts: offsets, then the permutation
+        rt::rt_scan_blocks<<<scan_blocks, 1024, 0, st>>>(W.bins, n_bins, r->w_bsums.p);
+        rt::rt_scan_sums<<<1, 1024, 0, st>>>(r->w_bsums.p, scan_blocks);
+        rt::rt_scan_add<<<scan_blocks, 1024, 0, st>>>(W.bins, n_bins, r->w_bsums.p);
+        rt::rt_scatter<<<blocks, 128, 0, st>>>(W.keys, W.bins, W.perm, n);
+        r->launches += 4;
+    };
+    WVB_CUDA(cudaMemsetAsync(W.bins, 0, (size_t)n_bins * 4, st));
+    rt::rt_wave_init<<<blocks, 128, 0, st>>>(r->sc, P, W, r->dirs.p, n);
+    r->launches++;
+    sort();
+    for (uint32_t step = 0; step <= P.depth; ++step) {
+        if (step < P.depth) WVB_CUDA(cudaMemsetAsync(W.bins, 0, (size_t)n_bins * 4, st));
+        rt::rt_wave<<<blocks, 128, 0, st>>>(r->sc, P, W, n, step, r->hist.p, r->dropped.p, d_refl, W.bins);
+        r->launches++;
+        if (step < P.depth) sort();
+    }
+}
+
 // Enqueues one trace of n rays on the handle's stream (no synchronisation):
 // directions from the host or generated, the rt_trace launch bracketed by the
 // handle's events, reflections of steps < keep into d_refl (device, [keep][n]).
@@ -125,10 +173,18 @@ void wvb_rt_trace_enqueue(wvb_rt* r, const wvb_rt_trace_params* p, const float* 
         rt::rt_directions<<<(n + 255) / 256, 256, 0, r->stream>>>(p->seed, p->ray_index_base, n, r->dirs.p);
         r->launches++;
     }
+    // One thread per ray life (rt_trace) for small batches, where the wavefront's ~6 launches
+    // per reflection would dominate; one launch per reflection with the rays re-binned in
+    // between (rt_wave) for large ones. params->mode can force either; results are the same.
+    const bool wave = p->mode == WVB_RT_MODE_WAVEFRONT || (p->mode == WVB_RT_MODE_AUTO && n >= (1u << 16));
     WVB_CUDA(cudaEventRecord(r->ev0, r->stream));
-    rt::rt_trace<<<(n + 127) / 128, 128, 0, r->stream>>>(r->sc, P, r->dirs.p, n, r->hist.p, r->dropped.p,
-                                                         P.keep_steps ? d_refl : nullptr);
-    r->launches++;
+    if (!wave) {
+        rt::rt_trace<<<(n + 127) / 128, 128, 0, r->stream>>>(r->sc, P, r->dirs.p, n, r->hist.p, r->dropped.p,
+                                                             P.keep_steps ? d_refl : nullptr);
+        r->launches++;
+    } else {
+        trace_wavefront(r, P, n, P.keep_steps ? d_refl : nullptr);
+    }
     WVB_CUDA(cudaEventRecord(r->ev1, r->stream));
     WVB_CUDA(cudaGetLastError());
 }

@@ -512,5 +512,244 @@ rt_trace(Scene sc, Params P, const float* __restrict__ dirs3, uint32_t n, double
     }
 }
 
+// ---------------------------------------------------------------------------
+// Wavefront form of the same loop: one launch per reflection, rays re-binned in between.
+//
+// rt_trace keeps 11 of 32 lanes busy on the concert hall (ncu): the lanes of a warp own
+// unrelated rays, so at any moment some step through empty voxels, some test triangles and some
+// are done. Here every ray's state lives in device memory; between two reflections the rays are
+// counting-sorted by (voxel of their origin, cell of their direction on an 8 x 8 octahedral
+// map), so that a warp's lanes start in the same voxel heading the same way and walk the same
+// cells. The receiver-visibility ray of a hit is cast at the START of the next pass, when the
+// rays are sorted by the voxel of that hit (all lanes then aim at the receiver from one voxel).
+// Per ray the arithmetic, its order and the random numbers (keyed by global ray index and step)
+// are those of rt_trace, so reflections and impulses are identical; only the order in which the
+// impulses reach the histogram's atomics differs (as it already does from run to run).
+// ---------------------------------------------------------------------------
+struct WaveState {
+    float4* pos;      // x, y, z of the ray origin (= last hit = path position), w = path distance
+    float4* dir;      // x, y, z, w = bits of the triangle just left (~0: none)
+    float4* vol;      // [2][n]: energy per band
+    uint32_t* alive;  // 1 while the ray is alive
+    uint32_t* keys;   // sort key of the next pass, per ray
+    uint32_t* perm;   // rays in the order of this pass
+    uint32_t* bins;   // counting-sort histogram / offsets, n_bins + 1 entries
+    uint32_t key_voxel_shift;  // voxel coordinates are coarsened by this many bits in the key
+    uint32_t key_side_bits;    // bits per (coarsened) voxel coordinate
+    uint32_t dead_key;         // key of a dead ray: the last bin
+};
+
+__device__ __forceinline__ uint32_t wave_key(const Scene& sc, const WaveState& W, f3 pos, f3 dir) {
+    const float sidef = (float)sc.side;
+    const int side = (int)sc.side;
+    int ix = (int)floorf((pos.x - sc.c0.x) / ((sc.c1.x - sc.c0.x) / sidef));
+    int iy = (int)floorf((pos.y - sc.c0.y) / ((sc.c1.y - sc.c0.y) / sidef));
+    int iz = (int)floorf((pos.z - sc.c0.z) / ((sc.c1.z - sc.c0.z) / sidef));
+    ix = min(max(ix, 0), side - 1) >> W.key_voxel_shift;
+    iy = min(max(iy, 0), side - 1) >> W.key_voxel_shift;
+    iz = min(max(iz, 0), side - 1) >> W.key_voxel_shift;
+    // octahedral map of the direction onto [-1, 1]^2, 8 x 8 cells
+    const float inv = 1.0f / (fabsf(dir.x) + fabsf(dir.y) + fabsf(dir.z));
+    float u = dir.x * inv, v = dir.y * inv;
+    if (dir.z < 0) {
+        const float uu = (1.0f - fabsf(v)) * (u < 0 ? -1.0f : 1.0f);
+        const float vv = (1.0f - fabsf(u)) * (v < 0 ? -1.0f : 1.0f);
+        u = uu;
+        v = vv;
+    }
+    const int cu = min(max((int)((u * 0.5f + 0.5f) * 8.0f), 0), 7);
+    const int cv = min(max((int)((v * 0.5f + 0.5f) * 8.0f), 0), 7);
+    const uint32_t voxel = (((uint32_t)ix << W.key_side_bits) | (uint32_t)iy) << W.key_side_bits | (uint32_t)iz;
+    return (voxel << 6) | (uint32_t)(cu * 8 + cv);
+}
+
+// pass 0 set-up: every ray at the source with its direction
+static __global__ void rt_wave_init(Scene sc, Params P, WaveState W, const float* __restrict__ dirs3, uint32_t n) {
+    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= n) return;
+    const f3 d = mk(dirs3[3 * (size_t)ri], dirs3[3 * (size_t)ri + 1], dirs3[3 * (size_t)ri + 2]);
+    W.pos[ri] = make_float4(P.source.x, P.source.y, P.source.z, 0.0f);
+    W.dir[ri] = make_float4(d.x, d.y, d.z, __uint_as_float(~0u));
+    W.vol[ri] = make_float4(P.ray_energy, P.ray_energy, P.ray_energy, P.ray_energy);
+    W.vol[(size_t)n + ri] = make_float4(P.ray_energy, P.ray_energy, P.ray_energy, P.ray_energy);
+    W.alive[ri] = 1u;
+    const uint32_t key = wave_key(sc, W, P.source, d);
+    W.keys[ri] = key;
+    atomicAdd(W.bins + key, 1u);
+}
+
+// exclusive scan of the bin counts, in place: 1024 threads x 4 bins per block
+static __global__ void __launch_bounds__(1024) rt_scan_blocks(uint32_t* __restrict__ bins, uint32_t n_bins,
+                                                              uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = base + k < n_bins ? bins[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (unsigned)o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_sums[threadIdx.x], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= (unsigned)o) wi += t;
+        }
+        warp_sums[threadIdx.x] = wi - w;  // exclusive prefix of the warps
+        if (threadIdx.x == 31) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[threadIdx.x >> 5] + incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n_bins) bins[base + k] = run;
+        run += v[k];
+    }
+}
+static __global__ void __launch_bounds__(1024) rt_scan_sums(uint32_t* __restrict__ block_sums, uint32_t n) {
+    // n <= 1024 * 8: one block, serial per thread + block scan
+    __shared__ uint32_t tot[1024];
+    const uint32_t per = (n + 1023u) / 1024u;
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t i = threadIdx.x * per + k;
+        if (i < n) s += block_sums[i];
+    }
+    tot[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint32_t t = threadIdx.x >= (unsigned)o ? tot[threadIdx.x - o] : 0u;
+        __syncthreads();
+        tot[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = tot[threadIdx.x] - s;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t i = threadIdx.x * per + k;
+        if (i < n) {
+            const uint32_t c = block_sums[i];
+            block_sums[i] = run;
+            run += c;
+        }
+    }
+}
+static __global__ void __launch_bounds__(1024) rt_scan_add(uint32_t* __restrict__ bins, uint32_t n_bins,
+                                                           const uint32_t* __restrict__ block_sums) {
+    const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n_bins) bins[base + k] += add;
+    }
+}
+static __global__ void rt_scatter(const uint32_t* __restrict__ keys, uint32_t* __restrict__ bins,
+                                  uint32_t* __restrict__ perm, uint32_t n) {
+    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri < n) perm[atomicAdd(bins + keys[ri], 1u)] = ri;
+}
+
+// one reflection of every ray, in sorted order. step == P.depth: only the deferred visibility
+// of the last hit.
+static __global__ void __launch_bounds__(128, RT_MIN_BLOCKS)
+rt_wave(Scene sc, Params P, WaveState W, uint32_t n, uint32_t step, double* __restrict__ hist,
+        unsigned long long* __restrict__ dropped, ReflectionPod* __restrict__ refl_out, uint32_t* __restrict__ next_bins) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t ri = W.perm[i];
+    if (!W.alive[ri]) {
+        if (step < P.depth) {
+            if (refl_out && step < P.keep_steps) refl_out[(size_t)step * n + ri] = ReflectionPod{};
+            W.keys[ri] = W.dead_key;
+            atomicAdd(next_bins + W.dead_key, 1u);
+        }
+        return;
+    }
+    const float4 p4 = W.pos[ri], d4 = W.dir[ri];
+    f3 rpos = mk(p4.x, p4.y, p4.z);
+    f3 rdir = mk(d4.x, d4.y, d4.z);
+    float path_dist = p4.w;
+    uint32_t prev_tri = __float_as_uint(d4.w);
+    float volume[8];
+    {
+        const float4 a = W.vol[ri], b = W.vol[(size_t)n + ri];
+        volume[0] = a.x; volume[1] = a.y; volume[2] = a.z; volume[3] = a.w;
+        volume[4] = b.x; volume[5] = b.y; volume[6] = b.z; volume[7] = b.w;
+    }
+    // ---- the previous reflection's visibility ray and diffuse contribution ----------------------
+    if (step > 0) {
+        const bool visible = point_visible(sc, rpos, P.receiver, prev_tri);
+        if (refl_out && step - 1 < P.keep_steps) refl_out[(size_t)(step - 1) * n + ri].receiver_visible = visible ? 1 : 0;
+        if (visible) {
+            const TriPre T = sc.pre[prev_tri];
+            const f3 tnorm_raw = mk(T.nx, T.ny, T.nz);
+            const float* sf = sc.surfaces + 16 * (size_t)sc.triangles[prev_tri].surface;
+            const f3 to_receiver = sub(P.receiver, rpos);
+            const float trd = length(to_receiver);
+            const float total = path_dist + trd;
+            const float cos_angle = fabsf(dot(tnorm_raw, normalize(to_receiver)));
+            const float sin_y = P.receiver_radius / fmaxf(P.receiver_radius, trd);
+            const float angle_correction = 1 - sqrtf(1 - sin_y * sin_y);
+            float out[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) out[b] = ((angle_correction * 2) * cos_angle) * (volume[b] * sf[8 + b]);
+            deposit(P, hist, dropped, out, rpos, total);
+        }
+    }
+    if (step >= P.depth) return;
+    // ---- this reflection ---------------------------------------------------------------------------
+    ReflectionPod refl = {};
+    uint32_t idx;
+    const float t = voxel_traversal(sc, rpos, rdir, prev_tri, idx);
+    uint32_t key = W.dead_key;
+    if (t) {
+        const f3 hit = add(rpos, mul(rdir, t));
+        const TriPre T = sc.pre[idx];
+        const f3 tnorm_raw = mk(T.nx, T.ny, T.nz);
+        const f3 specular = sub(rdir, mul(mul(tnorm_raw, 2), dot(rdir, tnorm_raw)));
+        const f3 tnorm = mul(tnorm_raw, signbit_scalar(dot(tnorm_raw, specular)));
+        float z, theta;
+        direction_rng(P.seed, (uint32_t)(P.ray_index_base + ri), step, 0u, z, theta);
+        const f3 rnd = sphere_point(z, theta);
+        const float* sf = sc.surfaces + 16 * (size_t)sc.triangles[idx].surface;
+        const float* sv = sf + 8;
+        const float scatter = (sv[0] + sv[1] + sv[2] + sv[3] + sv[4] + sv[5] + sv[6] + sv[7]) / 8;
+        const f3 l = mul(rnd, signbit_scalar(dot(rnd, tnorm)));
+        const f3 next = normalize(add(mul(l, scatter), mul(specular, 1 - scatter)));
+        refl.px = hit.x; refl.py = hit.y; refl.pz = hit.z;
+        refl.triangle = idx;
+        refl.keep_going = 1;
+        float last_volume[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            last_volume[b] = volume[b];
+            volume[b] = volume[b] * (1 - sf[b]);
+        }
+        const f3 last_position = rpos;
+        const float last_distance = path_dist;
+        const float this_distance = last_distance + length(sub(last_position, hit));
+        if (segment_sphere(last_position, hit, P.receiver, P.receiver_radius)) {
+            const float total = last_distance + length(sub(P.receiver, last_position));
+            if (step >= P.specular_from_step) deposit(P, hist, dropped, last_volume, last_position, total);
+        }
+        W.pos[ri] = make_float4(hit.x, hit.y, hit.z, this_distance);
+        W.dir[ri] = make_float4(next.x, next.y, next.z, __uint_as_float(idx));
+        W.vol[ri] = make_float4(volume[0], volume[1], volume[2], volume[3]);
+        W.vol[(size_t)n + ri] = make_float4(volume[4], volume[5], volume[6], volume[7]);
+        key = wave_key(sc, W, hit, next);
+    } else {
+        W.alive[ri] = 0u;
+    }
+    if (refl_out && step < P.keep_steps) refl_out[(size_t)step * n + ri] = refl;
+    W.keys[ri] = key;
+    atomicAdd(next_bins + key, 1u);
+}
+
 }  // namespace rt
 }  // namespace wvb

@@ -71,13 +71,15 @@ class RayTracer:
 
     def trace(self, dirs, source, receiver, depth, n_rays=None, total_rays=None, receiver_radius=0.1,
               speed_of_sound=340.0, histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0,
-              n_bins=None, directional=False, keep_steps=0):
+              n_bins=None, directional=False, keep_steps=0, mode=0):
         """dirs: n x 3 float32 or None (generate n_rays directions on the device).
+        mode: _lib.RT_MODE_* (0 = by batch size).
         Returns (reflections or None, dropped, device_ms); the histogram accumulates on the
         device, read it with histogram()."""
         d, n, P = self._params(dirs, source, receiver, depth, n_rays, total_rays, receiver_radius, speed_of_sound,
                                histogram_rate, seed, ray_index_base, specular_from_step, n_bins, directional,
                                keep_steps)
+        P.mode = int(mode)
         refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
         dropped, ms = C.c_uint64(0), C.c_float(0)
         check(lib().wvb_rt_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n,
@@ -181,12 +183,13 @@ class ImageSource:
 
     def trace(self, dirs, depth, order, n_rays=None, total_rays=None, receiver_radius=0.1, speed_of_sound=340.0,
               histogram_rate=1000.0, seed=1, ray_index_base=0, specular_from_step=0, n_bins=None,
-              directional=False, keep_steps=0):
+              directional=False, keep_steps=0, mode=0):
         """traces and feeds the tree on the device; returns the reflections of the first
         keep_steps steps (or None) for host-side consumers"""
         d, n, P = self.tracer._params(dirs, self.source, self.receiver, depth, n_rays, total_rays, receiver_radius,
                                       speed_of_sound, histogram_rate, seed, ray_index_base, specular_from_step,
                                       n_bins, directional, keep_steps)
+        P.mode = int(mode)
         refl = np.zeros((keep_steps, n), REFL_DT) if keep_steps else None
         dropped, ms = C.c_uint64(0), C.c_float(0)
         check(lib().wvb_is_trace(self._h, C.byref(P), ptr(d) if d is not None else None, n, int(order),
