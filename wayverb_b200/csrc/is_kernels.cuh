@@ -206,40 +206,65 @@ __device__ __forceinline__ bool cpu_intersects(const Scene& sc, const Ray& r, ui
         t_max[i] = isnan(tmp) ? INFINITY : tmp;
         t_delta[i] = fabsf(dm[i] / dir[i]);
     }
-    for (;;) {
-        int min_i = 0;
-        if (t_max[1] < t_max[min_i]) min_i = 1;
-        if (t_max[2] < t_max[min_i]) min_i = 2;
-        const float tm = min_i == 0 ? t_max[0] : (min_i == 1 ? t_max[1] : t_max[2]);
-        const uint2 cell = sc.cells[(size_t)ind[0] * side * side + (size_t)ind[1] * side + ind[2]];
-        const rt::VoxEntry* e = sc.entries + cell.x;
-        bool hit = false;
-        float best = 0.0f;
-        uint32_t best_i = 0;
-        for (uint32_t k = 0; k < cell.y; ++k) {
-            const uint32_t ti = e[k].tri;
-            if (ti == to_ignore) continue;
-            const float t = rt::tri_intersection(e[k].pre, r.pos, r.dir);
-            if (t != 0.0f && (!hit || t < best)) {
-                hit = true;
-                best = t;
-                best_i = ti;
+    // The host code nests "for each voxel { for each triangle }"; as in rt_kernels.cuh's
+    // voxel_traversal the walk runs here as a flat state machine paced by a warp vote -- per
+    // iteration a lane enters a voxel, tests ONE triangle of it, or leaves it; same visiting and
+    // testing order, same arithmetic -- so that the lanes of a warp work side by side instead of
+    // waiting for each other's inner loops.
+    const unsigned lanes = __activemask();
+    bool done = false, found = false, enter = true, hit = false;
+    int min_i = 0;
+    float tm = 0.0f, best = 0.0f;
+    uint32_t best_i = 0, k = 0, num = 0;
+    const rt::VoxEntry* e = sc.entries;
+    while (__any_sync(lanes, !done)) {
+        if (!done) {
+            if (enter) {
+                min_i = 0;
+                if (t_max[1] < t_max[min_i]) min_i = 1;
+                if (t_max[2] < t_max[min_i]) min_i = 2;
+                tm = min_i == 0 ? t_max[0] : (min_i == 1 ? t_max[1] : t_max[2]);
+                const uint2 cell = sc.cells[(size_t)ind[0] * side * side + (size_t)ind[1] * side + ind[2]];
+                e = sc.entries + cell.x;
+                num = cell.y;
+                k = 0;
+                hit = false;
+                best = 0.0f;
+                enter = false;
             }
-        }
-        if (hit && best <= tm) {
-            t_out = best;
-            index_out = best_i;
-            return true;
-        }
+            if (k < num) {
+                const uint32_t ti = e[k].tri;
+                if (ti != to_ignore) {
+                    const float t = rt::tri_intersection(e[k].pre, r.pos, r.dir);
+                    if (t != 0.0f && (!hit || t < best)) {
+                        hit = true;
+                        best = t;
+                        best_i = ti;
+                    }
+                }
+                ++k;
+            }
+            if (k >= num) {
+                if (hit && best <= tm) {
+                    t_out = best;
+                    index_out = best_i;
+                    found = true;
+                    done = true;
+                } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            if (i == min_i) {
-                ind[i] += step[i];
-                if (ind[i] == just_out[i]) return false;
-                t_max[i] += t_delta[i];
+                    for (int i = 0; i < 3; ++i) {
+                        if (i == min_i) {
+                            ind[i] += step[i];
+                            if (ind[i] == just_out[i]) done = true;
+                            t_max[i] += t_delta[i];
+                        }
+                    }
+                    enter = true;
+                }
             }
         }
     }
+    return found;
 }
 
 // ---- validation ------------------------------------------------------------------

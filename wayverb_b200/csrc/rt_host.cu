@@ -104,9 +104,16 @@ void trace_wavefront(wvb_rt* r, const rt::Params& P, uint32_t n, rt::ReflectionP
     uint32_t bits = 0;
     while ((1u << bits) < r->sc.side) ++bits;
     rt::WaveState W{};
-    W.key_voxel_shift = bits > 5 ? bits - 5 : 0;
-    W.key_side_bits = bits > 5 ? 5 : std::max(bits, 1u);
-    const uint32_t n_bins = (1u << (3 * W.key_side_bits + 6)) + 1;
+    // key = (voxel, direction cell), at most 21 bits: the counting sort's bin array stays in L2
+    uint32_t max_side_bits = 5, dir_bits = 3;
+#ifdef WVB_DEBUG_KNOBS
+    if (const char* v = getenv("WVB_RT_KEY_SIDE_BITS")) max_side_bits = (uint32_t)atoi(v);
+    if (const char* v = getenv("WVB_RT_KEY_DIR_BITS")) dir_bits = (uint32_t)atoi(v);
+#endif
+    W.key_voxel_shift = bits > max_side_bits ? bits - max_side_bits : 0;
+    W.key_side_bits = std::max(bits - W.key_voxel_shift, 1u);
+    W.key_dir_bits = dir_bits;
+    const uint32_t n_bins = (1u << (3 * W.key_side_bits + 2 * dir_bits)) + 1;
     W.dead_key = n_bins - 1;
     const uint32_t scan_blocks = (n_bins + 4095) / 4096;
     if (r->w_bins.n < n_bins) {

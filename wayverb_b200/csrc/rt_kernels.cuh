@@ -518,8 +518,7 @@ rt_trace(Scene sc, Params P, const float* __restrict__ dirs3, uint32_t n, double
 // rt_trace keeps 11 of 32 lanes busy on the concert hall (ncu): the lanes of a warp own
 // unrelated rays, so at any moment some step through empty voxels, some test triangles and some
 // are done. Here every ray's state lives in device memory; between two reflections the rays are
-// counting-sorted by (voxel of their origin, cell of their direction on an 8 x 8 octahedral
-// map), so that a warp's lanes start in the same voxel heading the same way and walk the same
+// counting-sorted by (voxel of their origin, cell of their direction on an octahedral map), so that a warp's lanes start in the same voxel heading the same way and walk the same
 // cells. The receiver-visibility ray of a hit is cast at the START of the next pass, when the
 // rays are sorted by the voxel of that hit (all lanes then aim at the receiver from one voxel).
 // Per ray the arithmetic, its order and the random numbers (keyed by global ray index and step)
@@ -536,6 +535,7 @@ struct WaveState {
     uint32_t* bins;   // counting-sort histogram / offsets, n_bins + 1 entries
     uint32_t key_voxel_shift;  // voxel coordinates are coarsened by this many bits in the key
     uint32_t key_side_bits;    // bits per (coarsened) voxel coordinate
+    uint32_t key_dir_bits;     // bits per axis of the octahedral direction map
     uint32_t dead_key;         // key of a dead ray: the last bin
 };
 
@@ -557,10 +557,11 @@ __device__ __forceinline__ uint32_t wave_key(const Scene& sc, const WaveState& W
         u = uu;
         v = vv;
     }
-    const int cu = min(max((int)((u * 0.5f + 0.5f) * 8.0f), 0), 7);
-    const int cv = min(max((int)((v * 0.5f + 0.5f) * 8.0f), 0), 7);
+    const int cells = 1 << W.key_dir_bits;
+    const int cu = min(max((int)((u * 0.5f + 0.5f) * (float)cells), 0), cells - 1);
+    const int cv = min(max((int)((v * 0.5f + 0.5f) * (float)cells), 0), cells - 1);
     const uint32_t voxel = (((uint32_t)ix << W.key_side_bits) | (uint32_t)iy) << W.key_side_bits | (uint32_t)iz;
-    return (voxel << 6) | (uint32_t)(cu * 8 + cv);
+    return (voxel << (2 * W.key_dir_bits)) | (uint32_t)(cu * cells + cv);
 }
 
 // pass 0 set-up: every ray at the source with its direction
