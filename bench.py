@@ -410,7 +410,8 @@ def ray_row(ctx, sampler, with_cpu):
     with wvb.RayTracer(sc, device=ctx.local) as g:
         if ctx.world > 1:
             g.comm_init(ctx.fresh_uid(), ctx.rank, ctx.world)
-        g.trace(None, src, rcv, depth, n_rays=1 << 14, total_rays=total, seed=1)      # warm-up
+        # warm-up with the batch size of the timed call (the schedule and its buffers depend on it)
+        g.trace(None, src, rcv, depth, n_rays=e - b, total_rays=total, seed=1, ray_index_base=b)
         if ctx.world > 1:
             g.allreduce_histogram()   # the communicator's first collective sets up its connections
         g.reset_histogram()

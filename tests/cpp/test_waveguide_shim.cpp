@@ -81,6 +81,27 @@ static int canonical_run(double b0) {
     }
     std::atomic_bool stop{false};
     if (!canonical(cc, m, source, receiver, env, 500.0, seconds, stop, no_pressure_callback{}).empty()) return 14;
+    // canonical.h:140-177, multi-band: one run per band with that band's flat coefficients; each band
+    // must equal the single-band run of a mesh carrying those coefficients
+    {
+        struct surf { struct { float s[8]; } absorption; };
+        const std::vector<surf> surfaces{{{{0.05f, 0.1f, 0.2f, 0.3f, 0.4f, 0.5f, 0.6f, 0.7f}}}};
+        const multiple_band_constant_spacing_parameters params{3, 500.0, 0.6};
+        const auto bands = canonical(cc, m, surfaces, source, receiver, env, params, seconds, true, no_pressure_callback{});
+        if (bands.size() != 3) return 17;
+        for (size_t band = 0; band < 3; ++band) {
+            auto mb = m;
+            mb.set_coefficients(to_flat_coefficients(surfaces[0].absorption.s[band]));
+            const auto one = canonical(cc, mb, source, receiver, env, 500.0, seconds, true, no_pressure_callback{});
+            if (one.size() != 1 || one[0].band.directional.size() != bands[band].band.directional.size()) return 18;
+            if (std::memcmp(one[0].band.directional.data(), bands[band].band.directional.data(),
+                            one[0].band.directional.size() * sizeof(one[0].band.directional[0]))) return 19;
+            if (std::fabs(bands[band].valid_hz.min - 20.0 * std::pow(1000.0, band / 8.0)) > 1e-9 ||
+                std::fabs(bands[band].valid_hz.max - 20.0 * std::pow(1000.0, (band + 1) / 8.0)) > 1e-9) return 20;
+        }
+        if (!std::memcmp(bands[0].band.directional.data(), bands[2].band.directional.data(),
+                         bands[0].band.directional.size() * sizeof(bands[0].band.directional[0]))) return 21;
+    }
     // cancellation DURING the device-side run: keep_going is polled every 64 steps (the reference
     // polls every step, waveguide.h:80) and the run returns the steps completed so far
     {

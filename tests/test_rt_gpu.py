@@ -204,13 +204,14 @@ def test_wavefront_dead_rays_directional_and_segments():
 def test_wavefront_on_the_concert_hall_with_image_sources():
     sc, meta = scene.concert_hall()
     src, rcv = meta["source"], meta["receiver"]
-    depth, order, n = wvb.reflection_depth(meta["min_absorption"]), 4, 70000   # above the automatic threshold
+    depth, order, n = wvb.reflection_depth(meta["min_absorption"]), 4, 70000
     o = rto.Scene(sc)
     d = rto.directions(0x5eed, n)
     want_h, want_r, _ = o.trace(d, src, rcv, depth, seed=0x5eed, specular_from_step=order + 1, keep_steps=order)
     want_i, _ = rto.image_source(o, rto.path_elements(want_r, order), src, rcv)
     with wvb.RayTracer(sc) as g, wvb.ImageSource(g, src, rcv, max_elements=n * order) as s:
-        got_r = s.trace(d, depth=depth, order=order, seed=0x5eed, specular_from_step=order + 1, keep_steps=order)
+        got_r = s.trace(d, depth=depth, order=order, seed=0x5eed, specular_from_step=order + 1, keep_steps=order,
+                        mode=_lib.RT_MODE_WAVEFRONT)
         got_h = g.histogram()
         got_i, _, _ = s.results()
     assert np.array_equal(got_r.view(np.uint8), want_r.view(np.uint8))
