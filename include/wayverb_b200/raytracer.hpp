@@ -656,9 +656,21 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
         core::detail::check(wvb_is_create(h.get(), &d, &is.h));
     }
 
+    // The reference traces 16384-ray segments one after the other (raytracer.h:219-262). The device
+    // wants far more rays in flight than that, and the result does not depend on how the rays are
+    // batched (random streams are keyed by global ray index), so several segments are traced in ONE
+    // device call and then handed to the processors segment by segment, with the per-segment
+    // callback and keep_going test in the reference's order. The batch is bounded by the
+    // reflection records that have to come back for host-side processors (<= 256 MB).
+    const size_t per_segment_bytes = std::max<size_t>(1, keep) * sizeof(reflection) * segment_size;
+    const size_t segments_per_batch = std::max<size_t>(1, std::min<size_t>(64, (size_t(256) << 20) / per_segment_bytes));
     std::vector<float> dirs;
     std::vector<reflection> refl;
-    const auto run_segment = [&](It b, size_t n, size_t base) {
+    // traces rays [base, base + n) and feeds them to the processors in segments of segment_size;
+    // returns false when keep_going was cleared after a full segment
+    const size_t groups = total / segment_size;
+    size_t group = 0;
+    const auto run_batch = [&](It b, size_t n, size_t base) -> bool {
         dirs.resize(n * 3);
         auto it = b;
         for (size_t i = 0; i < n; ++i, ++it) {
@@ -674,28 +686,35 @@ auto run(It b_direction, It e_direction, const core::compute_context& cc,
         } else {
             core::detail::check(wvb_rt_trace(h.get(), &p, dirs.data(), n, host_refl, nullptr, nullptr));
         }
-        detail::for_each_in(processors, [&](auto& proc, auto) {
-            auto group = proc.get_group_processor(n);
-            if (!detail::is_device_resident<std::decay_t<decltype(proc)>>::value) {
-                const size_t steps = std::min(keep, detail::steps_required_of(proc, depth, 0));
-                for (size_t s = 0; s < steps; ++s) {
-                    group.process(refl.begin() + s * n, refl.begin() + (s + 1) * n, buffers, s, depth);
+        for (size_t off = 0; off < n; off += segment_size) {
+            const size_t len = std::min(segment_size, n - off);
+            detail::for_each_in(processors, [&](auto& proc, auto) {
+                auto grp = proc.get_group_processor(len);
+                if (!detail::is_device_resident<std::decay_t<decltype(proc)>>::value) {
+                    const size_t steps = std::min(keep, detail::steps_required_of(proc, depth, 0));
+                    for (size_t s = 0; s < steps; ++s) {
+                        grp.process(refl.begin() + s * n + off, refl.begin() + s * n + off + len, buffers, s, depth);
+                    }
                 }
+                proc.accumulate(grp);
+            });
+            if (len == segment_size) {  // the tail segment has no callback (raytracer.h:246-262)
+                per_step_callback(group, groups);
+                ++group;
+                if (!keep_going) return false;
             }
-            proc.accumulate(group);
-        });
+        }
+        return true;
     };
 
-    const size_t groups = total / segment_size;
-    size_t done = 0, group = 0;
+    const size_t batch = segments_per_batch * segment_size;
     auto it = b_direction;
-    for (; done + segment_size <= total; done += segment_size, ++group) {
-        run_segment(it, segment_size, done);
-        std::advance(it, segment_size);
-        per_step_callback(group, groups);
-        if (!keep_going) return std::experimental::optional<return_type>{};
+    for (size_t done = 0; done < total;) {
+        const size_t n = std::min(batch, total - done);
+        if (!run_batch(it, n, done)) return std::experimental::optional<return_type>{};
+        std::advance(it, n);
+        done += n;
     }
-    if (done != total) run_segment(it, total - done, done);
 
     if (hist.present) {
         std::vector<double> hbuf(size_t(p.n_bins) * 8 * (hist.directional ? 180 : 1));
