@@ -374,57 +374,6 @@ inline size_t run_stock(const core::compute_context& cc, const mesh& mesh, size_
 
 // ---- stock processors (same behaviour as the reference's) ---------------------------------
 #ifdef WVB_WITH_REFERENCE_HEADERS
-/// simulation_parameters.h:9-44
-struct single_band_parameters final {
-    double cutoff;
-    double usable_portion;
-};
-struct multiple_band_constant_spacing_parameters final {
-    size_t bands;
-    double cutoff;
-    double usable_portion;
-};
-/// simulation_parameters.h:58-72
-constexpr double compute_cutoff_frequency(double sample_rate, double usable_portion) {
-    return sample_rate * 0.25 * usable_portion;
-}
-constexpr double compute_sampling_frequency(double cutoff, double usable_portion) {
-    return cutoff / (0.25 * usable_portion);
-}
-/// hrtf_band_params_hz().edges (hrtf/multiband.h:25-28, frequency_domain/envelope.cpp:46-49):
-/// 8 bands over 20 Hz - 20 kHz
-inline double hrtf_band_edge_hz(size_t edge) { return 20.0 * std::pow(20000.0 / 20.0, double(edge) / 8.0); }
-
-/// canonical.h:140-177, the multi-band variant: the waveguide is run once per band with every
-/// surface's flat coefficients for that band (set_flat_coefficients_for_band, :128-137), each
-/// band valid between the band's edges. `surfaces`: one entry per coefficient set of the mesh
-/// (the scene's surfaces, `.absorption.s[band]`). Empty on cancellation.
-template <typename Surfaces, typename PressureCallback>
-util::aligned::vector<bandpass_band> canonical(const core::compute_context& cc, mesh m, const Surfaces& surfaces,
-                                               const core::vec3& source, const core::vec3& receiver,
-                                               const core::environment& environment,
-                                               const multiple_band_constant_spacing_parameters& sim_params,
-                                               double simulation_time, const std::atomic_bool& keep_going,
-                                               PressureCallback&& pressure_callback) {
-    util::aligned::vector<bandpass_band> ret;
-    for (size_t b = 0; b != sim_params.bands; ++b) {
-        util::aligned::vector<coefficients_canonical> coeffs;
-        for (const auto& surface : surfaces) coeffs.push_back(to_flat_coefficients(surface.absorption.s[b]));
-        m.set_coefficients(std::move(coeffs));
-        band rendered;
-        if (!detail::canonical_impl(cc, m, simulation_time, source, receiver, environment, keep_going,
-                                    pressure_callback, rendered)) {
-            return {};
-        }
-        bandpass_band bb;
-        bb.band = std::move(rendered);
-        bb.valid_hz.min = hrtf_band_edge_hz(b);
-        bb.valid_hz.max = hrtf_band_edge_hz(b + 1);
-        ret.push_back(std::move(bb));
-    }
-    return ret;
-}
-
 }  // namespace waveguide
 }  // namespace wayverb
 // Overlay mode: the stock processors are the reference's OWN headers, compiled unmodified
