@@ -245,6 +245,54 @@ def boundary_coefficient_program() -> str:
     return unit("bcoef", parts, "bcoef_driver.inc")
 
 
+def function_source(rel: str, signature_regex: str) -> str:
+    """The text of one function definition of a reference .cpp file, from its signature to the
+    matching closing brace (taken where it lies, like the kernel strings)."""
+    text = _read(rel)
+    m = re.search(signature_regex, text)
+    if not m:
+        raise RuntimeError("no %s in %s" % (signature_regex, rel))
+    i = text.index("{", m.end() - 1)
+    depth, j = 0, i
+    while True:
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    return text[m.start():j + 1]
+
+
+def host_voxel_program() -> str:
+    """The reference's HOST voxelisation code (not OpenCL): compiled unmodified behind the GLM
+    stand-in of hoststubs/ -- tri_cube_intersection.cpp and the headers ndim_tree.h,
+    voxel_collection.h, indexing.h, utilities/range.h as whole files (#included where they lie),
+    geo::overlaps of box.cpp:21-27 and get_flattened of voxel_collection.cpp:9-37 as single
+    functions (the rest of those two files needs geometric.h / scene_data.h)."""
+    core = os.path.join(REF, "src", "core")
+    overlaps = function_source("src/core/src/geo/box.cpp", r"bool overlaps\(const box& b, const triangle_vec3& t\)\s*\{")
+    flattened = function_source("src/core/src/spatial_division/voxel_collection.cpp",
+                                r"util::aligned::vector<cl_uint> get_flattened\(\s*const voxel_collection<3>& voxels\)\s*\{")
+    return "\n".join([
+        "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+        "#include <array>", "#include <cmath>", "#include <functional>", "#include <memory>", "#include <numeric>",
+        "#include <stdexcept>", "#include <vector>",
+        '#include "glm/glm.hpp"',
+        '#include "core/geo/tri_cube_intersection.h"',
+        '#include "core/spatial_division/voxel_collection.h"',
+        '#include "%s"' % os.path.join(core, "src", "geo", "tri_cube_intersection.cpp"),
+        "namespace wayverb { namespace core { namespace geo {", overlaps, "} } }",
+        "namespace wayverb { namespace core {", flattened, "} }",
+        '#include "%s"' % os.path.join(HERE, "voxel_driver.inc"),
+    ]) + "\n"
+
+
+HOST_UNITS = {"ref_voxel.cpp": host_voxel_program}
+HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
+                 "-I", os.path.join(REF, "src", "utilities", "include")]
+
 UNITS = {
     "ref_wg_f32.cpp": lambda: waveguide_program(False),
     "ref_wg_f64.cpp": lambda: waveguide_program(True),
@@ -286,6 +334,16 @@ def build(force: bool = False) -> str | None:
             f.write(make())
         obj = path[:-4] + ".o"
         r = subprocess.run([CXX] + FLAGS + ["-c", path, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed on %s:\n%s" % (path, r.stderr[-6000:]))
+        objs.append(obj)
+    for fname, make in HOST_UNITS.items():
+        path = os.path.join(OUT, fname)
+        with open(path, "w") as f:
+            f.write(make())
+        obj = path[:-4] + ".o"
+        flags = ["-std=gnu++14", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"]
+        r = subprocess.run([CXX] + flags + HOST_INCLUDES + ["-c", path, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ failed on %s:\n%s" % (path, r.stderr[-6000:]))
         objs.append(obj)

@@ -104,6 +104,10 @@ def lib():
         L.refk_boundary_coefficient_finder_1d.argtypes = [vp, vp, vp, f, vp, vp, vp, u, vp, u, vp, sz, i]
         L.refk_boundary_coefficient_finder_2d.argtypes = [vp, vp, vp, f, vp, vp, sz]
         L.refk_boundary_coefficient_finder_3d.argtypes = [vp, vp, vp, f, vp, vp, sz]
+        L.refk_voxelise.restype = sz
+        L.refk_voxelise.argtypes = [vp, sz, vp, sz, sz, f, vp, vp, sz]
+        L.refk_overlaps.restype = i
+        L.refk_overlaps.argtypes = [vp, vp]
         for n, want in (("reflection", 32), ("ray", 32), ("surface", 64), ("triangle", 16), ("impulse", 64),
                         ("path_info", 64), ("mesh_descriptor", 48)):
             fn = getattr(L, "refk_sizeof_" + n)
@@ -339,3 +343,22 @@ def coefficient_indices(sc, nodes, min_corner, dims, spacing, n1, n2, n3):
     L.refk_boundary_coefficient_finder_2d(_p(nd), _p(mc), _p(d), float(spacing), _p(b2), _p(b1), nd.size)
     L.refk_boundary_coefficient_finder_3d(_p(nd), _p(mc), _p(d), float(spacing), _p(b3), _p(b1), nd.size)
     return b1[:n1], b2[:n2], b3[:n3]
+
+
+# ---- scene preparation (HOST code of the reference, compiled behind the GLM stand-in) ------------
+def voxelise(vertices4, triangles, depth=5, padding=0.1):
+    """make_voxelised_scene_data(scene, depth, padding) + get_flattened through the reference's own
+    ndim_tree / voxel_collection / tri_cube_intersection source -> (aabb[6], flattened index)."""
+    v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
+    t = np.ascontiguousarray(triangles).view(np.uint32).reshape(-1, 4)
+    aabb = np.zeros(6, np.float32)
+    n = lib().refk_voxelise(_p(v), v.shape[0], _p(t), t.shape[0], int(depth), float(padding), _p(aabb), None, 0)
+    out = np.zeros(n, np.uint32)
+    lib().refk_voxelise(_p(v), v.shape[0], _p(t), t.shape[0], int(depth), float(padding), _p(aabb), _p(out), n)
+    return aabb, out
+
+
+def overlaps(box6, tri9) -> bool:
+    b = np.ascontiguousarray(box6, np.float32).reshape(6)
+    t = np.ascontiguousarray(tri9, np.float32).reshape(9)
+    return bool(lib().refk_overlaps(_p(b), _p(t)))

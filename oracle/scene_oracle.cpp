@@ -15,12 +15,17 @@
 // eight children -- and then walked into the voxel grid; this is deliberately NOT the flat
 // descent of the product (wayverb_b200/csrc/scene_host.cpp).
 //
-// Parity pinning: the host C++ of the reference needs glm, which is not in this image, so it
-// cannot be compiled here as it stands. tests/test_scene.py pins this file (a) through
-// oracle/_ref's `ref_voxel` unit, which compiles the reference's own tri_cube_intersection.cpp,
-// ndim_tree.h, voxel_collection.h/.cpp behind a stand-in for the few glm operations they use,
-// where that unit is present, and (b) through the reference's own property tests
-// (core/tests/voxel_tests.cpp: voxel walk == brute force).
+// Parity pinning: PINNED to reference-run output, with one stated caveat. The reference's host C++
+// needs GLM, which is fetched at configure time and is not in this image; oracle/ref_recipe/build.py
+// compiles the reference's OWN tri_cube_intersection.cpp, ndim_tree.h, voxel_collection.h, indexing.h,
+// utilities/range.h, geo::overlaps (box.cpp:21-27) and get_flattened (voxel_collection.cpp:9-37),
+// unmodified and where they lie, behind a stand-in for the GLM operations they use
+// (oracle/ref_recipe/hoststubs/glm/glm.hpp: componentwise operators, dot, cross, normalize, min/max
+// after GLM 0.9.8.1's generic code paths -- the only arithmetic that stand-in decides).
+// tests/test_ref_pin_scene.py asserts that this file AND the product's wvb_voxelise reproduce that
+// build's flattened index entry for entry on the demo concert hall, its subdivided variants and
+// random triangle soups. On top: the reference's own property test (core/tests/voxel_tests.cpp:
+// voxel walk == brute force) on the same scenes, tests/test_scene.py, tests/test_config5_gpu.py.
 #include <array>
 #include <cmath>
 #include <cstdint>
