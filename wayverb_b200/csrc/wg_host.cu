@@ -36,7 +36,16 @@ void set_last_error(const char* fmt, ...) {
 }
 
 #ifndef WVB_TB2_THREADS
-#define WVB_TB2_THREADS 512
+#define WVB_TB2_THREADS 256
+#endif
+#ifndef WVB_TB2_TX
+#define WVB_TB2_TX 64
+#endif
+#ifndef WVB_TB2_MINB
+#define WVB_TB2_MINB 3
+#endif
+#ifndef WVB_TB2_NSTAGE
+#define WVB_TB2_NSTAGE 5
 #endif
 
 namespace {
@@ -297,9 +306,9 @@ int pick_zchunks(long long tiles, int nzl, int slots, int min_len) {
     return best;
 }
 
-void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows);
+void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows, int box_cols = 132);
 void make_tensor_map(wvb_wg* w, int which, int ty) { encode_plane_map(w, &w->map[which], w->P[which].p, ty + 2); }
-void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows) {
+void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows, int box_cols) {
     encode_tiled_fn enc = get_encode_tiled();
     WVB_REQUIRE(enc != nullptr, WVB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     const WgGeom& g = w->g;
@@ -307,7 +316,7 @@ void encode_plane_map(wvb_wg* w, CUtensorMap* map, double* base, int box_rows) {
     // overhang it are zero-filled by the TMA unit
     cuuint64_t gdim[3] = {(cuuint64_t)g.px, (cuuint64_t)g.py, (cuuint64_t)(g.nzl + 2)};
     cuuint64_t gstr[2] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.plane * 8};
-    cuuint32_t box[3] = {132, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -539,7 +548,7 @@ void enqueue_step(wvb_wg* w) {
 // Afterwards D is `current` and C `previous`: the handle's two arrays trade places with the two
 // scratch arrays (pointers and tensor maps), so everything else keeps addressing P[cur].
 void enqueue_pair(wvb_wg* w) {
-    using Cfg = Tb2Cfg<5, WVB_TB2_THREADS>;
+    using Cfg = Tb2Cfg<WVB_TB2_NSTAGE, WVB_TB2_THREADS, WVB_TB2_TX, WVB_TB2_MINB>;
     auto& tb = w->tb;
     const int ci = w->cur, pi = w->cur ^ 1;
     double* A = w->P[ci].p;
@@ -924,7 +933,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     if ((d->flags & WVB_WG_TEMPORAL2) || env_int("WVB_WG_TB2", 0)) {
         WVB_REQUIRE(d->nranks == 1 && tma_fits, WVB_ERR_UNSUPPORTED,
                     "WVB_WG_TEMPORAL2 needs a single-GPU handle and a mesh of at least 132 x 10 nodes per plane");
-        using Cfg = Tb2Cfg<5, WVB_TB2_THREADS>;
+        using Cfg = Tb2Cfg<WVB_TB2_NSTAGE, WVB_TB2_THREADS, WVB_TB2_TX, WVB_TB2_MINB>;
         auto& tb = w->tb;
         // class map with SHELL = an AIR node with a BOUNDARY node among its six neighbours
         auto cls_at = [&](int x, int y, int lz) -> int {
@@ -959,7 +968,7 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         encode_plane_map(w, &tb.one[0], tb.T[0].p, w->ty + 2);
         encode_plane_map(w, &tb.one[1], tb.T[1].p, w->ty + 2);
         double* arr[4] = {w->P[0].p, w->P[1].p, tb.T[0].p, tb.T[1].p};
-        for (int i = 0; i < 4; ++i) encode_plane_map(w, &tb.wide[i], arr[i], Cfg::TY + 4);
+        for (int i = 0; i < 4; ++i) encode_plane_map(w, &tb.wide[i], arr[i], Cfg::TY + 4, Cfg::BOXX);
         WVB_CUDA(cudaFuncSetAttribute(wg_air_tb2<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)Cfg::SMEM_BYTES));
         int occ = 0;

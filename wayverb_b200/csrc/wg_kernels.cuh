@@ -483,27 +483,28 @@ wg_air_tma(const __grid_constant__ CUtensorMap cur_map, double* __restrict__ pre
 // ---------------------------------------------------------------------------
 enum : uint8_t { CLS_SHELL = 3 };  // TB2's class map only: AIR with a BOUNDARY neighbour
 
-template <int NSTAGE_, int THREADS_>
+template <int NSTAGE_, int THREADS_, int TX_ = 128, int MINB_ = 2>
 struct Tb2Cfg {
-    static constexpr int TX = 128, TY = 8;
+    static constexpr int TX = TX_, TY = 8;
+    static constexpr int MINB = MINB_;
     static constexpr int NSTAGE = NSTAGE_;       // level-0 ring: 3 live planes + prefetch
     static constexpr int BOXX = TX + 4, BOXY = TY + 4;
     static constexpr int THREADS = THREADS_;
     static constexpr int L1_PAIRS = (BOXX / 2) * (TY + 2);          // 66 x 10 = 660
     static constexpr int L1_PER_THREAD = (L1_PAIRS + THREADS - 1) / THREADS;
-    static constexpr int ROW_GROUPS = THREADS / 64;                  // owned rows handled side by side
+    static constexpr int ROW_GROUPS = THREADS / (TX / 2);             // owned rows handled side by side
     static constexpr int L2_PER_THREAD = TY / ROW_GROUPS;
     static constexpr uint32_t BOX_BYTES = BOXX * BOXY * 8;           // 12 672
     static constexpr uint32_t STAGE_BYTES = (BOX_BYTES + 127u) & ~127u;
     static constexpr uint32_t SMEM_BYTES = (NSTAGE + 3) * STAGE_BYTES + NSTAGE * 8 + 128;
     static_assert(NSTAGE >= 4, "three live level-0 planes + at least one in flight");
-    static_assert(THREADS % 64 == 0 && TY % ROW_GROUPS == 0, "thread count must tile the rows");
+    static_assert(THREADS % (TX / 2) == 0 && TY % ROW_GROUPS == 0, "thread count must tile the rows");
 };
 
 // one pair of nodes: v = third(sum of six ports) - p, the arithmetic of update_pair
+template <uint32_t ROW>
 __device__ __forceinline__ void tb2_pair(uint32_t sb, uint32_t sm, uint32_t sa, double2 p, double& v0,
                                          double& v1, double& s0, double& s1) {
-    constexpr uint32_t ROW = (128 + 4) * 8;
     const double2 mid = tma::lds2(sm);
     const double l = tma::lds1(sm - 8);
     const double r = tma::lds1(sm + 16);
@@ -528,7 +529,7 @@ __device__ __forceinline__ void store_unless_boundary(double* dst, double v0, do
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 2)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__ Bp, double* __restrict__ Cp,
            double* __restrict__ Dp, const uint8_t* __restrict__ code, WgGeom g, int tiles_x, int tiles_y,
            int zchunks, int* __restrict__ flag) {
@@ -585,7 +586,7 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
         ko1[k] = in_mesh ? (uint32_t)((long long)(zs - 1) * g.cplane + (long long)y * g.pc + (x >> 1)) : 0u;
     }
     // ---- owned pairs (level 2): pair column tx, rows ty + RG rr ------------------------------------
-    const int tx = tid & 63, ty = tid >> 6;
+    const int tx = tid % (TX / 2), ty = tid / (TX / 2);
     const int x = x0 + 2 * tx;
     const uint32_t so2 = (uint32_t)(((ty + 2) * BOXX + 2 * tx + 2) * 8);
     bool valid2[K2];
@@ -669,7 +670,7 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
             if ((c0 | c1b) & 1u) {  // AIR = 1, SHELL = 3: odd
                 const double2 p = pB[k];
                 double s0, s1;
-                tb2_pair(s_lo + so1[k], s_mid + so1[k], s_hi + so1[k], p, v0, v1, s0, s1);
+                tb2_pair<BOXX * 8>(s_lo + so1[k], s_mid + so1[k], s_hi + so1[k], p, v0, v1, s0, s1);
                 if (!(c0 & 1u)) v0 = 0.0;
                 if (!(c1b & 1u)) v1 = 0.0;
                 if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
@@ -699,7 +700,7 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
                 if (c0 == CLS_AIR || c1b == CLS_AIR) {
                     const double2 p = tma::lds2(s_lo + o);  // p(n) of the pair: level-0 plane z
                     double s0, s1;
-                    tb2_pair(l1_b + o, l1_m + o, l1_q + o, p, v0, v1, s0, s1);
+                    tb2_pair<BOXX * 8>(l1_b + o, l1_m + o, l1_q + o, p, v0, v1, s0, s1);
                     if (c0 != CLS_AIR) v0 = 0.0;
                     if (c1b != CLS_AIR) v1 = 0.0;
                     if (max(abs_hi(v0), abs_hi(v1)) >= 0x7ff00000u) {
