@@ -122,6 +122,7 @@ struct wvb_wg {
     int bminb = 4;
     int bpipe = 4;  // >0: pipelined 1-d boundary walk with this many blocks per SM
     int bthreads = 128;
+    int tb_b1_small = 0, tb_b1_blocks = 1;
     int air_first = 1;
     dev_buf<uint32_t> step_counter;
     int use_graph = 1;
@@ -425,6 +426,24 @@ void launch_boundary_sep(wvb_wg* w, const double* cur, double* prev, double* out
     launch_boundary_t<128, 4, true, true>(w, cur, prev, st, out);
     w->launches++;
 }
+// The same update with a footprint that fits NEXT TO three wg_air_tb2 CTAs on an SM (two warps,
+// <= 128 registers, one block per SM striding over the 1-d list, and the fused kernel's
+// L1 / shared-memory split so that the SM need not drain to take it): the fused kernel is bound
+// by instruction issue, not by HBM, so the walls' first step can run underneath it.
+void launch_boundary_sep_small(wvb_wg* w, const double* cur, double* prev, double* out, cudaStream_t st) {
+    if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WVB_CUDA(cudaFuncSetAttribute(wg_boundary_all<64, 8, true, true>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 72));
+        attr_set = true;
+    }
+    const int saved = w->bpipe;
+    w->bpipe = w->tb_b1_blocks;
+    launch_boundary_t<64, 8, true, true>(w, cur, prev, st, out);
+    w->bpipe = saved;
+    w->launches++;
+}
 
 void launch_boundary(wvb_wg* w, const double* cur, double* prev, cudaStream_t st) {
     if (!(w->bl[0].n + w->bl[1].n + w->bl[2].n)) return;
@@ -560,10 +579,13 @@ void enqueue_pair(wvb_wg* w) {
     const int tiles_x = (g.dx + Cfg::TX - 1) / Cfg::TX, tiles_y = (g.dy + Cfg::TY - 1) / Cfg::TY;
     WVB_CUDA(cudaEventRecord(w->ev_fork, w->stream));
     WVB_CUDA(cudaStreamWaitEvent(w->stream_b, w->ev_fork, 0));
+    // p(n+1) on the walls: first, so that its one small block per SM is resident when the fused
+    // kernel's CTAs arrive
+    if (has_boundary && w->tb_b1_small) launch_boundary_sep_small(w, A, B, C, w->stream_b);
     wg_air_tb2<Cfg><<<(unsigned)(tiles_x * tiles_y * tb.zchunks), Cfg::THREADS, Cfg::SMEM_BYTES, w->stream>>>(
             tb.wide[ci], B, C, D, tb.code.p, g, tiles_x, tiles_y, tb.zchunks, w->flag.p);
     w->launches++;
-    if (has_boundary) launch_boundary_sep(w, A, B, C, w->stream_b);  // p(n+1) on the walls
+    if (has_boundary && !w->tb_b1_small) launch_boundary_sep(w, A, B, C, w->stream_b);
     WVB_CUDA(cudaEventRecord(w->ev_join, w->stream_b));
     WVB_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
     // C is complete: shell nodes and the walls' second step, side by side
@@ -976,6 +998,8 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
         const long long tb_tiles = (long long)((dx + Cfg::TX - 1) / Cfg::TX) * ((dy + Cfg::TY - 1) / Cfg::TY);
         const int tb_zc = env_int("WVB_WG_TB2_ZCHUNKS", 0);
         tb.zchunks = tb_zc > 0 ? std::min(tb_zc, g.nzl) : pick_zchunks(tb_tiles, g.nzl, std::max(1, occ) * w->sm_count, 24);
+        w->tb_b1_small = env_int("WVB_WG_TB2_B1SMALL", 0);  // measured slower (0.67 / 0.60 vs 0.564 ms/step)
+        w->tb_b1_blocks = env_int("WVB_WG_TB2_B1BLOCKS", 1);
         tb.on = true;
     }
 

@@ -621,9 +621,18 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
     fetch_level1(zs - 1);
     fetch_level2(koff2);
     // iteration z: level 1 of plane q = z + 1, then level 2 of plane z (if z >= zs).
-    // Level-0 plane p sits in stage (p - (zs - 2)) % NS, level-1 plane q in stage (q + 3) % 3.
-    int st0 = 0;          // stage of level-0 plane z
-    uint32_t ph0 = 0;     // phase bits, one per stage (bit s = parity to wait for next)
+    // Level-0 plane p sits in stage (p - (zs - 2)) % NS; the level-1 planes rotate through three
+    // buffers. Ring state is kept as running shared-memory addresses (no multiplies or modulo in
+    // the loop): s_lo / s_mid / s_hi = level-0 planes z, z+1, z+2; l1_b / l1_m / l1_q = level-1
+    // planes z-1, z, z+1.
+    uint32_t s_lo = base, s_mid = base + Cfg::STAGE_BYTES, s_hi = base + 2 * Cfg::STAGE_BYTES;
+    uint32_t bar_lo = bars, bar_hi = bars + 16;
+    const uint32_t ring_end = base + NS * Cfg::STAGE_BYTES, bars_end = bars + 8 * NS;
+    uint32_t ph_hi = 0;    // parity to wait for on the barrier of plane z + 2
+    uint32_t l1_b = l1base + Cfg::STAGE_BYTES, l1_m = l1base + 2 * Cfg::STAGE_BYTES, l1_q = l1base;
+    // planes zs-2 and zs-1 (the first two boxes) before the loop; plane z+2 inside it
+    tma::mbar_wait(bars, 0u);
+    tma::mbar_wait(bars + 8, 0u);
     for (int z = zs - 2; z < ze; ++z) {
         const int q = z + 1;
         double2 pB[K1];
@@ -641,24 +650,8 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
         for (int rr = 0; rr < K2; ++rr) c2[rr] = c2_next[rr];
         if (q < ze) fetch_level1(q + 1);
         if (z >= zs && z + 1 < ze) fetch_level2(koff2 + ksp);
-        // the three level-0 planes z, z+1, z+2: wait for z+2 (earlier ones were waited for before),
-        // on the first iteration for all three
-        {
-            const int first = (z == zs - 2) ? 0 : 2;
-            for (int d = first; d < 3; ++d) {
-                int st = st0 + d;
-                if (st >= NS) st -= NS;
-                tma::mbar_wait(bars + 8 * st, (ph0 >> st) & 1u);
-                ph0 ^= 1u << st;
-            }
-        }
-        int sg1 = st0 + 1, sg2 = st0 + 2;
-        if (sg1 >= NS) sg1 -= NS;
-        if (sg2 >= NS) sg2 -= NS;
-        const uint32_t s_lo = base + st0 * Cfg::STAGE_BYTES, s_mid = base + sg1 * Cfg::STAGE_BYTES,
-                       s_hi = base + sg2 * Cfg::STAGE_BYTES;
+        tma::mbar_wait(bar_hi, ph_hi);
         // ---- level 1 of plane q -------------------------------------------------------------------
-        const uint32_t l1_q = l1base + (uint32_t)((q + 3) % 3) * Cfg::STAGE_BYTES;
         const bool q_owned = q >= zs && q < ze;
 #pragma unroll
         for (int k = 0; k < K1; ++k) {
@@ -686,8 +679,6 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
         __syncthreads();  // level-1 plane q complete
         // ---- level 2 of plane z ----------------------------------------------------------------------
         if (z >= zs) {
-            const uint32_t l1_b = l1base + (uint32_t)((z + 2) % 3) * Cfg::STAGE_BYTES;  // plane z - 1
-            const uint32_t l1_m = l1base + (uint32_t)((z + 3) % 3) * Cfg::STAGE_BYTES;  // plane z
 #pragma unroll
             for (int rr = 0; rr < K2; ++rr) {
                 if (!valid2[rr]) continue;
@@ -716,11 +707,26 @@ wg_air_tb2(const __grid_constant__ CUtensorMap a_map, const double* __restrict__
         }
         __syncthreads();  // level-0 plane z and level-1 plane z - 1 are free
         if (tid == 0 && issued < n_planes) {
-            tma::mbar_arrive_expect_tx(bars + 8 * st0, Cfg::BOX_BYTES);
-            tma::load_box_3d(base + st0 * Cfg::STAGE_BYTES, &a_map, bars + 8 * st0, bx, by, zs - 2 + issued);
+            tma::mbar_arrive_expect_tx(bar_lo, Cfg::BOX_BYTES);
+            tma::load_box_3d(s_lo, &a_map, bar_lo, bx, by, zs - 2 + issued);
             ++issued;
         }
-        st0 = sg1;
+        // rotate the rings
+        s_lo = s_mid;
+        s_mid = s_hi;
+        s_hi += Cfg::STAGE_BYTES;
+        bar_lo += 8;
+        bar_hi += 8;
+        if (s_hi == ring_end) s_hi = base;
+        if (bar_lo == bars_end) bar_lo = bars;
+        if (bar_hi == bars_end) {  // the barrier of plane z + 2 wrapped: the next phase of the ring
+            bar_hi = bars;
+            ph_hi ^= 1u;
+        }
+        const uint32_t l1_free = l1_b;
+        l1_b = l1_m;
+        l1_m = l1_q;
+        l1_q = l1_free;
     }
     raise_flags(bad, flag);
 }
