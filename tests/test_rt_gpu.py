@@ -217,3 +217,33 @@ def test_wavefront_on_the_concert_hall_with_image_sources():
     assert np.array_equal(got_r.view(np.uint8), want_r.view(np.uint8))
     assert np.abs(got_h - want_h).max() <= 1e-9 * np.abs(want_h).max()
     assert np.array_equal(got_i.view(np.uint8), want_i.view(np.uint8))
+
+
+def test_occluder_lying_on_a_voxel_face():
+    """the visibility ray stops walking at the receiver's distance, the reference walks
+    to the grid's edge; the two agree as long as voxel lists are conservative. A panel lying
+    EXACTLY on a voxel face (x = 2.0 with the grid [-0.1, 4.1] / 4) between source and receiver is
+    the case where a sloppy list would show: octree-voxelised (the panel is listed on both sides
+    of the face) the records, visibility flags included, equal the oracle's full walk."""
+    base = scene.box_scene(BOX, subdiv=1, side=4)
+    v = [tuple(p[:3]) for p in base.vertices]
+    t = [tuple(int(c) for c in r) for r in base.triangles.tolist()]
+    n0 = len(v)
+    v += [(2.0, 0.5, 1.0), (2.0, 2.5, 1.0), (2.0, 2.5, 5.0), (2.0, 0.5, 5.0)]
+    t += [(0, n0, n0 + 1, n0 + 2), (0, n0, n0 + 2, n0 + 3)]
+    sc = scene.Scene(np.array(v, np.float32), np.array(t, np.uint32).view(scene.TRI_DT).reshape(-1),
+                     [scene.make_surface(0.1, 0.3)], pad=0.1, voxeliser="octree", depth=2)
+    assert sc.side == 4 and np.isclose((sc.aabb[3] - sc.aabb[0]) / 4 * 2 + sc.aabb[0], 2.0)
+    src, rcv = (0.9, 1.4, 2.8), (3.2, 1.6, 3.1)     # the panel stands between them
+    n, depth = 40000, 12
+    d = rto.directions(21, n)
+    want_h, want_r, _ = rto.Scene(sc).trace(d, src, rcv, depth, seed=21, keep_steps=depth)
+    for mode in (_lib.RT_MODE_RAY_LIFE, _lib.RT_MODE_WAVEFRONT):
+        with wvb.RayTracer(sc) as g:
+            got_r, _, _ = g.trace(d, src, rcv, depth, seed=21, keep_steps=depth, mode=mode)
+            got_h = g.histogram()
+        assert np.array_equal(got_r.view(np.uint8), want_r.view(np.uint8))
+        assert_hist_close(got_h, want_h)
+    vis = want_r["receiver_visible"][want_r["keep_going"] == 1]
+    assert 0.1 < vis.mean() < 0.9          # the panel hides the receiver from many hits, not from all
+    assert (want_r["triangle"] >= 12).any()  # and is hit itself
