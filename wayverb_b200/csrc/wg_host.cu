@@ -125,6 +125,23 @@ struct wvb_wg {
     int tb_b1_small = 0, tb_b1_blocks = 1;
     int air_first = 1;
     dev_buf<uint32_t> step_counter;
+    // Receiver cache of the per-step path: waveguide::run's post callback reads the same few nodes
+    // of `current` after every launch (postprocessor::node: 1, directional_receiver: 7), each read
+    // a blocking round trip in the reference (cl/common.h:42-47). wvb_wg_launch gathers the nodes
+    // that were asked for after the previous launch along with the error flag, in the same
+    // device-to-host copy and the same synchronisation; wvb_wg_read_f64 answers from that copy
+    // while nothing has written to the handle since. `current` is not modified by the kernel, so
+    // the values are exactly what a read after the launch returns.
+    static constexpr int RC_MAX = 16;
+    int rc_n = 0, rc_dirty = 0, rc_valid = 0;
+    uint64_t rc_nodes[RC_MAX];
+    int rc_owned[RC_MAX];
+    long long rc_offs[RC_MAX];
+    dev_buf<long long> d_rc_offs;
+    dev_buf<double> d_rc_vals;
+    double* h_rc_vals = nullptr;  // pinned, RC_MAX doubles
+    unsigned long long* h_seq = nullptr;  // pinned: sequence number of the last finished per-step launch
+    unsigned long long seq = 0;
     int use_graph = 1;
     cudaGraphExec_t step_graph = nullptr;  // two plain steps starting from P[0] = current
 
@@ -183,6 +200,8 @@ struct wvb_wg {
         if (stream_c) cudaStreamDestroy(stream_c);
         if (stream) cudaStreamDestroy(stream);
         if (h_flag) cudaFreeHost(h_flag);
+        if (h_rc_vals) cudaFreeHost(h_rc_vals);
+        if (h_seq) cudaFreeHost(h_seq);
     }
 };
 
@@ -887,6 +906,11 @@ void create_impl(const wvb_wg_desc* d, wvb_wg* w) {
     w->bthreads = env_int("WVB_WG_BTHREADS", 128);
     w->air_first = env_int("WVB_WG_AIRFIRST", 1);
     WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_flag), 8 * sizeof(int)));
+    WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_rc_vals), wvb_wg::RC_MAX * sizeof(double)));
+    WVB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->h_seq), sizeof(unsigned long long)));
+    *w->h_seq = 0;
+    w->d_rc_offs.alloc(wvb_wg::RC_MAX, true, &w->device_bytes);
+    w->d_rc_vals.alloc(wvb_wg::RC_MAX, true, &w->device_bytes);
     w->P[0].alloc((size_t)total, true, &w->device_bytes);
     w->P[1].alloc((size_t)total, true, &w->device_bytes);
     w->code.upload(code.data(), code.size(), &w->device_bytes);
@@ -1139,6 +1163,7 @@ void wvb_wg_destroy(wvb_wg* wg) { delete wg; }
 
 wvb_status wvb_wg_write_f64(wvb_wg* w, uint64_t node, double value) {
     if (!w) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         const long long off = local_offset(w, node, nullptr);
@@ -1153,12 +1178,31 @@ wvb_status wvb_wg_write_f64(wvb_wg* w, uint64_t node, double value) {
 
 wvb_status wvb_wg_read_f64(wvb_wg* w, uint64_t node, double* value, int* owned) {
     if (!w || !value) return WVB_ERR_INVALID;
+    if (w->rc_valid) {  // gathered with the last launch's flag: no round trip
+        for (int i = 0; i < w->rc_n; ++i) {
+            if (w->rc_nodes[i] == node) {
+                *value = w->h_rc_vals[i];
+                if (owned) *owned = w->rc_owned[i];
+                return WVB_OK;
+            }
+        }
+    }
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         int own = 0;
         const long long off = local_offset(w, node, &own);
         if (owned) *owned = own;
         *value = 0.0;
+        // remember the node: the next launch brings its value along with the flag
+        bool known = false;
+        for (int i = 0; i < w->rc_n; ++i) known = known || w->rc_nodes[i] == node;
+        if (!known && w->rc_n < wvb_wg::RC_MAX) {
+            w->rc_nodes[w->rc_n] = node;
+            w->rc_owned[w->rc_n] = own;
+            w->rc_offs[w->rc_n] = off;   // -1: no local copy
+            w->rc_n++;
+            w->rc_dirty = 1;
+        }
         if (off < 0) return;
         WVB_CUDA(cudaMemcpyAsync(value, w->P[w->cur].p + off, sizeof(double), cudaMemcpyDeviceToHost,
                                  w->stream));
@@ -1215,6 +1259,7 @@ wvb_status wvb_wg_read_field_f32(wvb_wg* w, float* out) {
 
 wvb_status wvb_wg_write_field(wvb_wg* w, const double* in) {
     if (!w || !in) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         double* cur = w->P[w->cur].p;
@@ -1226,6 +1271,7 @@ wvb_status wvb_wg_write_field(wvb_wg* w, const double* in) {
 
 wvb_status wvb_wg_step(wvb_wg* w, uint32_t n_steps, int32_t* error_flags) {
     if (!w) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     int flags = 0;
     wvb_status s = guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
@@ -1245,12 +1291,49 @@ wvb_status wvb_wg_step(wvb_wg* w, uint32_t n_steps, int32_t* error_flags) {
 wvb_status wvb_wg_launch(wvb_wg* w, int32_t* error_flags) {
     if (!w) return WVB_ERR_INVALID;
     int flags = 0;
+    w->rc_valid = 0;
     wvb_status s = guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         WVB_CUDA(cudaMemsetAsync(w->flag.p, 0, sizeof(int), w->stream));
         enqueue_launch(w);
-        WVB_CUDA(cudaGetLastError());
-        flags = fetch_flags(w);
+        if (w->rc_dirty && w->rc_n) {
+            WVB_CUDA(cudaMemcpyAsync(w->d_rc_offs.p, w->rc_offs, w->rc_n * sizeof(long long),
+                                     cudaMemcpyHostToDevice, w->stream));
+            w->rc_dirty = 0;
+        }
+        if (w->nranks == 1) {
+            // flag + the nodes `post` asked for last time (from `current`, which the kernel only reads)
+            // written by the device into pinned host memory; the host spins on the sequence number
+            const unsigned long long seq = ++w->seq;
+            wg_finish<<<1, 32, 0, w->stream>>>(w->P[w->cur].p, w->d_rc_offs.p, w->rc_n, w->flag.p, w->h_rc_vals,
+                                               w->h_flag, w->h_seq, seq);
+            w->launches++;
+            WVB_CUDA(cudaGetLastError());
+            volatile unsigned long long* vs = w->h_seq;
+            for (unsigned spins = 0; *vs != seq; ++spins) {
+                if ((spins & 0xfffu) == 0xfffu) {  // a faulting kernel never writes: ask the runtime now and then
+                    const cudaError_t q = cudaStreamQuery(w->stream);
+                    if (q != cudaErrorNotReady) {
+                        WVB_CUDA(q);
+                        break;  // finished between the two looks
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            flags = *(volatile int*)w->h_flag;
+        } else {
+            if (w->rc_n) {
+                wg_gather_now<<<1, 32, 0, w->stream>>>(w->P[w->cur].p, w->d_rc_offs.p, w->rc_n, w->d_rc_vals.p);
+                w->launches++;
+                WVB_CUDA(cudaMemcpyAsync(w->h_rc_vals, w->d_rc_vals.p, w->rc_n * sizeof(double),
+                                         cudaMemcpyDeviceToHost, w->stream));
+            }
+            WVB_CUDA(cudaGetLastError());
+            flags = fetch_flags(w);  // synchronises the stream: flag and gathered values are on the host
+        }
+        if (w->rc_n) w->rc_valid = 1;
     });
     if (error_flags) *error_flags = flags;
     if (s == WVB_OK && flags) {
@@ -1262,12 +1345,14 @@ wvb_status wvb_wg_launch(wvb_wg* w, int32_t* error_flags) {
 
 wvb_status wvb_wg_swap(wvb_wg* w) {
     if (!w) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     w->cur ^= 1;
     return WVB_OK;
 }
 
 wvb_status wvb_wg_time_steps(wvb_wg* w, uint32_t n_steps, float* ms, int32_t* error_flags) {
     if (!w || !ms) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     int flags = 0;
     wvb_status s = guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
@@ -1288,6 +1373,7 @@ wvb_status wvb_wg_time_steps(wvb_wg* w, uint32_t n_steps, float* ms, int32_t* er
 
 wvb_status wvb_wg_time_kernels(wvb_wg* w, uint32_t n, float ms[2]) {
     if (!w || !ms) return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     return guarded([&] {
         WVB_CUDA(cudaSetDevice(w->dev));
         const double* cur = w->P[w->cur].p;
@@ -1353,6 +1439,7 @@ wvb_status wvb_wg_run(wvb_wg* w, const wvb_wg_run_params* p, uint32_t* steps_don
                       int32_t* error_flags) {
     if (!w || !p || (p->n_steps && !p->signal) || (p->n_receivers && (!p->receiver_nodes || !p->out)))
         return WVB_ERR_INVALID;
+    w->rc_valid = 0;
     int flags = 0;
     uint32_t done = 0;
     wvb_status s = guarded([&] {

@@ -1079,6 +1079,25 @@ __global__ void wg_gather(const double* __restrict__ cur, const long long* __res
     if (i < n) out[(size_t)(*step_ptr) * n + i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
 }
 __global__ void wg_advance(uint32_t* __restrict__ step_ptr) { *step_ptr += 1; }
+// End of a per-step launch on a single-GPU handle: the error flag and the cached receiver values
+// go straight into mapped pinned host memory, followed (after a system-scope fence) by a sequence
+// number the host spins on -- no copy commands, no stream synchronisation on the per-step path.
+__global__ void wg_finish(const double* __restrict__ cur, const long long* __restrict__ offs, int n,
+                          const int* __restrict__ flag, volatile double* host_vals, volatile int* host_flag,
+                          volatile unsigned long long* host_seq, unsigned long long seq) {
+    const int i = threadIdx.x;
+    if (i < n) host_vals[i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
+    if (i == 0) *host_flag = *flag;
+    __threadfence_system();
+    __syncwarp();
+    if (i == 0) *host_seq = seq;
+}
+// the same gather without a step index: out[i] = cur[offs[i]] (0 where this slab holds no copy)
+__global__ void wg_gather_now(const double* __restrict__ cur, const long long* __restrict__ offs, int n,
+                              double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i < n) out[i] = offs[i] >= 0 ? cur[offs[i]] : 0.0;
+}
 
 // ---------------------------------------------------------------------------
 // Ghost-plane exchange over peer-mapped memory (NVLink / NVSwitch), no NCCL call per step.
