@@ -62,6 +62,57 @@ def ray_check(rank, world, local):
     return ok
 
 
+def per_step_check(rank, world, local):
+    """the per-step path on slabs (what waveguide::run drives): write / launch / read / swap on every
+    rank, the error flag gathered over peer memory and the receiver answered from the launch's cache;
+    receiver samples against the single-domain oracle, and an inf planted on rank 0 must raise the
+    flag on EVERY rank in the same step"""
+    ok = True
+    for halo in (_lib.HALO_AUTO, _lib.HALO_NCCL):
+        dims = (140, 40, 10 * world + 4)
+        box = [wvb.waveguide.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        dx, dy, dz = dims
+        z0, z1 = wvb.slab_range(dz, rank, world)
+        lo, hi = max(z0 - 1, 0), min(z1 + 1, dz)
+        mesh = wvb.cuboid_mesh(dims, [plaster()], z0=lo, nz=hi - lo)
+        src = mesh.index(dx // 2, dy // 2, wvb.slab_range(dz, 0, world)[1] - 1)
+        rcv = mesh.index(dx // 2 + 3, dy // 2 - 2, dz - 4)          # in the last slab
+        steps = 3 * dz
+        got = np.zeros(steps)
+        with wvb.Waveguide(mesh, device=local, z_range=(z0, z1), rank=rank, nranks=world, nccl_unique_id=box[0],
+                           kernel=_lib.KERNEL_TMA, flags=halo) as g:
+            for s in range(steps):
+                g.write(src, 1.0 if s == 0 else 0.0)
+                assert g.launch() == 0
+                got[s] = g.read(rcv)      # 0 on ranks that do not own the node
+                g.swap()
+            # error flag: inf on rank 0's source node; every rank must see it after the same launch
+            g.write(src, float("inf"))
+            flags = []
+            for s in range(3):
+                flags.append(g.launch())
+                g.swap()
+            halo_name = g.info()["halo"]
+        t = torch.from_numpy(got).cuda()
+        dist.all_reduce(t)
+        fl = torch.tensor(flags, device="cuda")
+        all_fl = [torch.zeros_like(fl) for _ in range(world)]
+        dist.all_gather(all_fl, fl)
+        if rank == 0:
+            om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [plaster()])
+            sim = wgo.Sim(om)
+            sig = np.zeros(steps)
+            sig[0] = 1.0
+            _, want, _ = sim.run(src, sig, [rcv], soft=False)
+            same = np.array_equal(t.cpu().numpy(), want[:, 0])
+            same_flags = all(torch.equal(all_fl[0], f) for f in all_fl) and int(all_fl[0][0]) != 0
+            print("per-step path, halo %s, ranks %d: receiver samples identical=%s, error flags equal on all ranks=%s %s"
+                  % (halo_name, world, same, same_flags, all_fl[0].tolist()), flush=True)
+            ok = ok and same and same_flags and np.abs(want).max() > 0
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -115,6 +166,7 @@ def main():
             print("dims %s kernel %s halo %s ranks %d: field identical=%s (rel RMS %.1e), traces identical=%s"
                   % (dims, info["kernel_variant"], info["halo"], world, same_f, rms, same_o), flush=True)
             ok = ok and same_f and same_o and wflag == 0
+    ok = per_step_check(rank, world, local) and ok
     ok = ray_check(rank, world, local) and ok
     res = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(res, 0)

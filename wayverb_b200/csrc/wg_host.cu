@@ -172,6 +172,14 @@ struct wvb_wg {
         int zchunks = 1;
         uint64_t pairs = 0;
     } tb;
+    // error-flag all-gather over peer memory (wg_xflag_publish / wg_xflag_finish)
+    struct xflags_t {
+        bool on = false;
+        dev_buf<unsigned long long> mine;             // [nranks], slot r written by rank r
+        std::vector<unsigned long long*> peer;        // mapped arrays of all ranks (own entry = mine.p)
+        dev_buf<unsigned long long*> d_peer;
+        unsigned long long seq = 0;
+    } xf;
     dev_buf<unsigned long long> halo_flags;    // [0] written by the rank below, [1] by the rank above
     dev_buf<unsigned long long> halo_counter;  // exchanges done
     dev_buf<unsigned int> halo_ticket;
@@ -187,6 +195,9 @@ struct wvb_wg {
             for (void* q : {(void*)p->P[0], (void*)p->P[1], (void*)p->flags}) {
                 if (q) cudaIpcCloseMemHandle(q);
             }
+        }
+        for (size_t r = 0; r < xf.peer.size(); ++r) {
+            if ((int)r != rank && xf.peer[r]) cudaIpcCloseMemHandle(xf.peer[r]);
         }
         if (comm && nccl::get().ok) nccl::get().CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
@@ -686,6 +697,59 @@ struct halo_blob {
     cudaIpcMemHandle_t p0, p1, flags;
     int32_t nzl, ok;
 };
+// Every rank maps every other rank's flag array: the per-step error-flag reduction then is N
+// eight-byte stores and a short spin instead of an ncclAllReduce. Collective; leaves xf.on false
+// (the NCCL reduction stays in use) if any rank fails to map any array.
+void setup_xflags(wvb_wg* w) {
+    auto& n = nccl::get();
+    auto& xf = w->xf;
+    const int N = w->nranks;
+    if (N > 32) return;
+    xf.mine.alloc((size_t)N, true, &w->device_bytes);
+    cudaIpcMemHandle_t mine{};
+    int good = cudaIpcGetMemHandle(&mine, xf.mine.p) == cudaSuccess ? 1 : 0;
+    if (!good) cudaGetLastError();
+    dev_buf<cudaIpcMemHandle_t> d_mine, d_all;
+    d_mine.upload(&mine, 1);
+    d_all.alloc((size_t)N, true);
+    nccl_check(n.GroupStart(), "ncclGroupStart");
+    for (int r = 0; r < N; ++r) {
+        if (r == w->rank) continue;
+        nccl_check(n.Send(d_mine.p, sizeof(cudaIpcMemHandle_t), nccl::t_uint8, r, w->comm, w->stream), "ncclSend");
+        nccl_check(n.Recv(d_all.p + r, sizeof(cudaIpcMemHandle_t), nccl::t_uint8, r, w->comm, w->stream), "ncclRecv");
+    }
+    nccl_check(n.GroupEnd(), "ncclGroupEnd");
+    std::vector<cudaIpcMemHandle_t> all((size_t)N);
+    WVB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, (size_t)N * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost,
+                             w->stream));
+    WVB_CUDA(cudaStreamSynchronize(w->stream));
+    xf.peer.assign((size_t)N, nullptr);
+    xf.peer[(size_t)w->rank] = xf.mine.p;
+    for (int r = 0; r < N && good; ++r) {
+        if (r == w->rank) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            good = 0;
+        }
+        xf.peer[(size_t)r] = static_cast<unsigned long long*>(q);
+    }
+    dev_buf<int> d_good;
+    d_good.upload(&good, 1);
+    nccl_check(n.AllReduce(d_good.p, d_good.p, 1, nccl::t_int32, nccl::op_min, w->comm, w->stream), "ncclAllReduce");
+    int all_good = 0;
+    WVB_CUDA(cudaMemcpyAsync(&all_good, d_good.p, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    WVB_CUDA(cudaStreamSynchronize(w->stream));
+    if (!all_good) {
+        for (int r = 0; r < N; ++r) {
+            if (r != w->rank && xf.peer[(size_t)r]) cudaIpcCloseMemHandle(xf.peer[(size_t)r]);
+        }
+        xf.peer.clear();
+        return;
+    }
+    xf.d_peer.upload(xf.peer.data(), xf.peer.size(), &w->device_bytes);
+    xf.on = true;
+}
 bool setup_p2p(wvb_wg* w) {
     auto& n = nccl::get();
     w->halo_flags.alloc(2, true, &w->device_bytes);
@@ -746,6 +810,7 @@ bool setup_p2p(wvb_wg* w) {
     int all_good = 0;
     WVB_CUDA(cudaMemcpyAsync(&all_good, d_good.p, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     WVB_CUDA(cudaStreamSynchronize(w->stream));
+    if (all_good) setup_xflags(w);
     if (!all_good) {
         for (wvb_wg::peer_t* p : {&w->below, &w->above}) {
             for (void* q : {(void*)p->P[0], (void*)p->P[1], (void*)p->flags}) {
@@ -1323,6 +1388,33 @@ wvb_status wvb_wg_launch(wvb_wg* w, int32_t* error_flags) {
 #endif
             }
             flags = *(volatile int*)w->h_flag;
+        } else if (w->xf.on) {
+            // the same finish with the flags of all ranks gathered over peer memory
+            const unsigned long long seq = ++w->seq;
+            const unsigned long long xseq = ++w->xf.seq;
+            wg_xflag_publish<<<1, 32, 0, w->stream>>>(w->flag.p, w->xf.d_peer.p, w->nranks, w->rank, xseq);
+            wg_xflag_finish<<<1, 32, 0, w->stream>>>(w->xf.mine.p, w->nranks, xseq, w->P[w->cur].p, w->d_rc_offs.p,
+                                                     w->rc_n, w->h_rc_vals, w->h_flag, w->h_seq, seq);
+            w->launches += 2;
+            WVB_CUDA(cudaGetLastError());
+            volatile unsigned long long* vs = w->h_seq;
+            for (unsigned spins = 0; *vs != seq; ++spins) {
+                if ((spins & 0xfffu) == 0xfffu) {
+                    const cudaError_t q = cudaStreamQuery(w->stream);
+                    if (q != cudaErrorNotReady) {
+                        WVB_CUDA(q);
+                        break;
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            flags = *(volatile int*)w->h_flag;
+            if (flags & WVB_FLAG_HALO_TIMEOUT) {
+                set_last_error("a rank stopped delivering (ghost planes or error flags timed out)");
+                throw status_error{WVB_ERR_NCCL};
+            }
         } else {
             if (w->rc_n) {
                 wg_gather_now<<<1, 32, 0, w->stream>>>(w->P[w->cur].p, w->d_rc_offs.p, w->rc_n, w->d_rc_vals.p);
