@@ -175,7 +175,7 @@ struct wvb_wg {
     // error-flag all-gather over peer memory (wg_xflag_publish / wg_xflag_finish)
     struct xflags_t {
         bool on = false;
-        dev_buf<unsigned long long> mine;             // [nranks], slot r written by rank r
+        dev_buf<unsigned long long> mine;             // [2][nranks], slot r of a set written by rank r
         std::vector<unsigned long long*> peer;        // mapped arrays of all ranks (own entry = mine.p)
         dev_buf<unsigned long long*> d_peer;
         unsigned long long seq = 0;
@@ -705,7 +705,7 @@ void setup_xflags(wvb_wg* w) {
     auto& xf = w->xf;
     const int N = w->nranks;
     if (N > 32) return;
-    xf.mine.alloc((size_t)N, true, &w->device_bytes);
+    xf.mine.alloc((size_t)N * 2, true, &w->device_bytes);  // two alternating sets of N slots
     cudaIpcMemHandle_t mine{};
     int good = cudaIpcGetMemHandle(&mine, xf.mine.p) == cudaSuccess ? 1 : 0;
     if (!good) cudaGetLastError();

@@ -1178,12 +1178,16 @@ __global__ void wg_halo_wait(const unsigned long long* __restrict__ flags, int h
 // like the ghost planes): wg_xflag_publish stores (sequence << 32 | this rank's error flag) into slot
 // [rank] of every rank's array -- one 8-byte store each, so value and sequence arrive together --
 // and wg_xflag_finish waits until all slots of the local array carry this launch's sequence, ORs
-// the flags and finishes like wg_finish. An all-gather of one word over NVLink in a few
+// the flags and finishes like wg_finish. Two sets of slots, used alternately: a fast rank may
+// publish launch k+1 while a slow one is still reading the slots of launch k, but nobody can
+// publish k+2 before everybody has published k+1, i.e. has finished reading k. An all-gather of one word over NVLink in a few
 // microseconds instead of an ncclAllReduce + copy + stream synchronisation per step.
 __global__ void wg_xflag_publish(const int* __restrict__ flag, unsigned long long* const* __restrict__ peers,
                                  int nranks, int rank, unsigned long long seq) {
     const int p = threadIdx.x;
-    if (p < nranks) st_release_sys(peers[p] + rank, (seq << 32) | (unsigned long long)(unsigned)(*flag));
+    if (p < nranks) {
+        st_release_sys(peers[p] + (seq & 1ull) * nranks + rank, (seq << 32) | (unsigned long long)(unsigned)(*flag));
+    }
 }
 __global__ void wg_xflag_finish(const unsigned long long* __restrict__ mine, int nranks, unsigned long long seq,
                                 const double* __restrict__ cur, const long long* __restrict__ offs, int n,
@@ -1194,7 +1198,7 @@ __global__ void wg_xflag_finish(const unsigned long long* __restrict__ mine, int
     if (i < nranks) {
         const unsigned long long t0 = global_timer_ns();
         unsigned long long v;
-        while (((v = ld_acquire_sys(mine + i)) >> 32) != (seq & 0xffffffffull)) {
+        while (((v = ld_acquire_sys(mine + (seq & 1ull) * nranks + i)) >> 32) != (seq & 0xffffffffull)) {
             __nanosleep(64);
             if (global_timer_ns() - t0 > 20ull * 1000 * 1000 * 1000) {  // a rank died: do not hang
                 v = (unsigned long long)WVB_FLAG_HALO_TIMEOUT;
