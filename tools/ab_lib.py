@@ -1,5 +1,8 @@
-"""A/B of two builds of libwvb200.so on the SAME box (boxes differ by ~8 %):
-alternates the libraries in fresh processes and prints the step time of each.
+"""A/B of two builds of libwvb200.so on the SAME box (boxes differ by ~8 %). Arms given as
+environment settings need a library built with -DWVB_DEBUG_KNOBS (the shipped one ignores them):
+    WVB_LIB_OUT=$PWD/wayverb_b200/libwvb200_dbg.so WVB_NVCC_DEFS=-DWVB_DEBUG_KNOBS python -m wayverb_b200.build
+    WVB_LIB=$PWD/wayverb_b200/libwvb200_dbg.so python tools/ab_lib.py default WVB_WG_BPIPE=2
+It alternates the libraries in fresh processes and prints the step time of each.
 usage: ab_lib.py A B [C ...] [rounds]   where each arm is a library path or a
 comma-separated list of environment settings (WVB_WG_BPIPE=4,WVB_WG_BMINB=4)."""
 import os

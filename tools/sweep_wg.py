@@ -1,4 +1,5 @@
-"""Times the waveguide step for kernel variants / tile parameters on one GPU.
+"""Times the waveguide step for kernel variants / tile parameters on one GPU (needs a library built
+with -DWVB_DEBUG_KNOBS and WVB_LIB pointing at it: the shipped library ignores the WVB_WG_* knobs).
 Development tool (not the bench): prints Mnode-updates/s and the 32 B/node
 bandwidth figure for each configuration."""
 import json
