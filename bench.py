@@ -592,19 +592,43 @@ def main():
 
     # ---- BASELINE's other multi-GPU shapes + the ray loop ----------------------------------
     extras = {}
+
+    def extra(name, fn):
+        """one optional row; on a single GPU a failure is recorded instead of losing the headline
+        (with several ranks an exception on one of them cannot be contained: it propagates)"""
+        if world > 1:
+            extras[name] = fn()
+            return
+        try:
+            extras[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if not args.no_extras:
         k = min(args.steps, 200)
         if (sx, sy, sz) == (512, 512, 512):
-            extras["config4"] = time_mesh(ctx, (512, 512, 2048), coeffs, k, args.warmup, sampler)
-            extras["config4"]["what"] = "BASELINE config 4's mesh split over the %d rank(s)" % world
+            def config4():
+                r = time_mesh(ctx, (512, 512, 2048), coeffs, k, args.warmup, sampler)
+                r["what"] = "BASELINE config 4's mesh split over the %d rank(s)" % world
+                return r
+
+            def strong():
+                r = time_mesh(ctx, (512, 512, 512), coeffs, k, args.warmup, sampler)
+                r["what"] = "the 512^3 mesh split over the %d ranks (strong scaling)" % world
+                return r
+
+            def slab256():
+                r = time_mesh(ctx, (512, 512, 256), coeffs, k, args.warmup, sampler)
+                r["what"] = ("the 256-plane slab one GPU of config 4 owns, alone on one GPU: "
+                             "8x this rate is config 4's ideal")
+                return r
+
+            extra("config4", config4)
             if world > 1:
-                extras["strong"] = time_mesh(ctx, (512, 512, 512), coeffs, k, args.warmup, sampler)
-                extras["strong"]["what"] = "the 512^3 mesh split over the %d ranks (strong scaling)" % world
+                extra("strong", strong)
             else:
-                extras["slab256"] = time_mesh(ctx, (512, 512, 256), coeffs, k, args.warmup, sampler)
-                extras["slab256"]["what"] = ("the 256-plane slab one GPU of config 4 owns, alone on one GPU: "
-                                             "8x this rate is config 4's ideal")
-        extras["ray"] = ray_row(ctx, sampler, with_cpu=(world == 1 and not args.no_cpu_baseline))
+                extra("slab256", slab256)
+        extra("ray", lambda: ray_row(ctx, sampler, with_cpu=(world == 1 and not args.no_cpu_baseline)))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -681,7 +705,10 @@ def main():
             line["multi_gpu_parity"] = parity
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     if ctx.dist:
         ctx.dist.barrier()
