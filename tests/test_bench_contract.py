@@ -128,3 +128,23 @@ def test_a_failing_optional_row_does_not_cost_the_headline(monkeypatch):
     d = run_bench(monkeypatch, boom)
     assert d["ray"] == {"error": "RuntimeError: boom"}
     assert d["value"] > 0 and "roofline" in d
+
+
+def test_reference_arm_runs_on_the_host_and_prints_the_contract():
+    """`bench.py --impl reference` for real (CPU only): the reference's own kernel source from
+    oracle/_ref (or the oracle port where that is absent), every host thread even when the
+    launcher exported OMP_NUM_THREADS=1 like torch.distributed.run does"""
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "Mnode-updates/s (fp64)" and d["unit"] == "Mnode-updates/s"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    threads = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == threads, "the arm must not inherit OMP_NUM_THREADS=1"
