@@ -15,11 +15,14 @@ Where the reference is not reproducible the same stated replacements as in the p
     uniform u_k, x = 1 - u_k in (0, 1] (the reference's uniform_real_distribution{1.0, 0.0});
   * log(1 / x) is evaluated by a fixed series (neg_log_fixed) in plain double arithmetic, and
     pow(t, 2.0) as t * t, so that the event times do not depend on a libm.
-Parity pinning: the FFT filter needs fftw3 and the reference's host code needs glm: neither is
-here, so this file is pinned only by the reference's own property test
-(raytracer/tests/stochastic_tests.cpp / frequency_domain tests: band magnitudes sum to 1 across
-the crossover, filtered energy splits between bands) restated in tests/test_pp.py, and by the
-closed-form checks there (event-rate law, energy conservation of weight_sequence).
+Parity pinning: PINNED to reference-run output. oracle/ref_recipe/build.py compiles the reference's own
+postprocessing.cpp, frequency_domain library, hrtf/multiband.h, core/sinc.h and crossover_filter,
+unmodified, behind an FFTW stand-in (hoststubs/fftw3.h) and with the engine's seed chosen;
+tests/test_ref_pin_pp.py asserts this file bit-identical to that build for the rate law, the event
+loop (dirac_sequence(intervals=...): the reference's arithmetic on the reference engine's numbers),
+weight_sequence, band edges, magnitudes and the window, and within float rounding (5e-7 of the peak)
+for everything that passes through a transform. On top: the reference's own property tests restated
+in tests/test_pp.py (band magnitudes sum to 1 across the crossover, energy splits between bands).
 """
 from __future__ import annotations
 
@@ -80,17 +83,23 @@ def t0(constant):
     return math.pow(2.0 * math.log(2.0) / constant, 1.0 / 3.0)
 
 
-def dirac_sequence(speed_of_sound, room_volume, sample_rate, max_time, seed=1):
-    """-> (float32 sequence, events drawn)"""
+def dirac_sequence(speed_of_sound, room_volume, sample_rate, max_time, seed=1, intervals=None):
+    """-> (float32 sequence, events drawn)
+
+    intervals=None: the stated replacements (Philox uniforms, fixed -log series, t * t).
+    intervals=array: the unit-rate draws log(1 / x) are taken from the caller and pow(t, 2.0) from
+    libm -- the reference's own arithmetic, so that tests/test_ref_pin_pp.py can hold this loop
+    against the reference's generate_dirac_sequence run with the same engine."""
     c = constant_mean_event_occurrence(speed_of_sound, room_volume)
     ret = np.zeros(int(math.ceil(max_time * sample_rate)), np.float32)
-    exps = exponentials(seed, int(min(1.5 * 10000.0 * max_time + 4096.0, 2.0e9)))
+    ref_arith = intervals is not None
+    exps = intervals if ref_arith else exponentials(seed, int(min(1.5 * 10000.0 * max_time + 4096.0, 2.0e9)))
     t, k = t0(c), 0
     while t < max_time:
         sample_index = t * sample_rate
         twice = int(2 * sample_index)
         ret[int(sample_index)] = -1.0 if twice % 2 else 1.0
-        mean = min(c * (t * t), 10000.0)
+        mean = min(c * (math.pow(t, 2.0) if ref_arith else t * t), 10000.0)
         t += exps[k] / mean
         k += 1
     return ret, k

@@ -289,9 +289,45 @@ def host_voxel_program() -> str:
     ]) + "\n"
 
 
-HOST_UNITS = {"ref_voxel.cpp": host_voxel_program}
+def host_pp_program() -> str:
+    """The reference's HOST post-processing code: raytracer/src/stochastic/postprocessing.cpp and the
+    whole frequency_domain library as files (#included where they lie) over the FFTW stand-in of
+    hoststubs/fftw3.h, plus crossover_filter of combined/postprocess.h:33-60 as a single function
+    (the rest of that header needs the waveguide / raytracer engines). std::random_device is spelled
+    as a device that returns a chosen seed while postprocessing.cpp is read, nothing else changes."""
+    src = os.path.join(REF, "src")
+    crossover = function_source("src/combined/include/combined/postprocess.h",
+                                r"template <typename LoIt, typename HiIt>\s*auto crossover_filter\(")
+    fd = os.path.join(src, "frequency_domain", "src")
+    return "\n".join([
+        "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+        "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <complex>", "#include <cstring>",
+        "#include <functional>", "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <random>",
+        "#include <stdexcept>", "#include <vector>",
+        "static unsigned refk_pp_seed_value = 1;",
+        "namespace std { struct refk_seeded_device { unsigned operator()() const { return refk_pp_seed_value; } }; }",
+        "#define random_device refk_seeded_device",
+        '#include "%s"' % os.path.join(src, "raytracer", "src", "stochastic", "postprocessing.cpp"),
+        "#undef random_device",
+        '#include "%s"' % os.path.join(fd, "envelope.cpp"),
+        '#include "%s"' % os.path.join(fd, "traits.cpp"),
+        '#include "%s"' % os.path.join(fd, "buffer.cpp"),
+        '#include "%s"' % os.path.join(fd, "plan.cpp"),
+        '#include "%s"' % os.path.join(fd, "filter.cpp"),
+        '#include "utilities/aligned/vector.h"',
+        '#include "core/sinc.h"',
+        '#include "core/sum_ranges.h"',
+        "namespace wayverb { namespace combined {", crossover, "} }",
+        '#include "%s"' % os.path.join(HERE, "pp_driver.inc"),
+    ]) + "\n"
+
+
+HOST_UNITS = {"ref_voxel.cpp": host_voxel_program, "ref_pp.cpp": host_pp_program}
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
-                 "-I", os.path.join(REF, "src", "utilities", "include")]
+                 "-I", os.path.join(REF, "src", "utilities", "include"),
+                 "-I", os.path.join(REF, "src", "raytracer", "include"),
+                 "-I", os.path.join(REF, "src", "frequency_domain", "include"),
+                 "-I", os.path.join(REF, "src", "hrtf", "lib", "include")]
 
 UNITS = {
     "ref_wg_f32.cpp": lambda: waveguide_program(False),

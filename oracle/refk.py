@@ -108,6 +108,22 @@ def lib():
         L.refk_voxelise.argtypes = [vp, sz, vp, sz, sz, f, vp, vp, sz]
         L.refk_overlaps.restype = i
         L.refk_overlaps.argtypes = [vp, vp]
+        d = C.c_double
+        L.refk_pp_rate_law.argtypes = [d, d, d, vp]
+        L.refk_pp_intervals.argtypes = [u, sz, vp, vp]
+        L.refk_pp_dirac_sequence.restype = sz
+        L.refk_pp_dirac_sequence.argtypes = [u, d, d, d, d, vp, sz]
+        for n in ("weight_sequence", "postprocessing"):
+            getattr(L, "refk_pp_" + n).restype = sz
+            getattr(L, "refk_pp_" + n).argtypes = [vp, sz, d, vp, sz, d, d, vp, sz]
+        L.refk_pp_multiband_mixdown.argtypes = [vp, sz, d, vp]
+        L.refk_pp_band_params.argtypes = [d, vp, vp]
+        L.refk_pp_magnitudes.argtypes = [d, d, d, d, sz, vp]
+        L.refk_pp_crossover.restype = sz
+        L.refk_pp_crossover.argtypes = [vp, sz, vp, sz, d, d, vp]
+        L.refk_pp_left_hanning.argtypes = [sz, vp]
+        L.refk_pp_fft_length.restype = sz
+        L.refk_pp_fft_length.argtypes = [sz]
         for n, want in (("reflection", 32), ("ray", 32), ("surface", 64), ("triangle", 16), ("impulse", 64),
                         ("path_info", 64), ("mesh_descriptor", 48)):
             fn = getattr(L, "refk_sizeof_" + n)
@@ -362,3 +378,85 @@ def overlaps(box6, tri9) -> bool:
     b = np.ascontiguousarray(box6, np.float32).reshape(6)
     t = np.ascontiguousarray(tri9, np.float32).reshape(9)
     return bool(lib().refk_overlaps(_p(b), _p(t)))
+
+
+# ---- post-processing (HOST code of the reference: stochastic/postprocessing.cpp, frequency_domain) ----
+def pp_rate_law(speed_of_sound, room_volume, t):
+    """-> (constant_mean_event_occurrence, mean_event_occurrence(constant, t), t0(constant))"""
+    out = np.zeros(3, np.float64)
+    lib().refk_pp_rate_law(float(speed_of_sound), float(room_volume), float(t), _p(out))
+    return tuple(out)
+
+
+def pp_intervals(seed, n):
+    """interval_size(engine, 1.0) n times for std::default_random_engine{seed} -> (log(1 / x), x)"""
+    iv, xs = np.zeros(n, np.float64), np.zeros(n, np.float64)
+    lib().refk_pp_intervals(int(seed), n, _p(iv), _p(xs))
+    return iv, xs
+
+
+def pp_dirac_sequence(seed, speed_of_sound, room_volume, sample_rate, max_time):
+    """generate_dirac_sequence with its engine seeded by `seed` instead of std::random_device"""
+    args = (int(seed), float(speed_of_sound), float(room_volume), float(sample_rate), float(max_time))
+    n = lib().refk_pp_dirac_sequence(*args, None, 0)
+    out = np.zeros(n, np.float32)
+    lib().refk_pp_dirac_sequence(*args, _p(out), n)
+    return out
+
+
+def _pp_hist_seq(histogram, sequence):
+    h = np.ascontiguousarray(np.asarray(histogram, np.float64).reshape(-1, 8).astype(np.float32))
+    return h, np.ascontiguousarray(sequence, np.float32)
+
+
+def pp_weight_sequence(histogram, hist_rate, sequence, seq_rate, acoustic_impedance):
+    h, s = _pp_hist_seq(histogram, sequence)
+    out = np.zeros((s.size, 8), np.float32)
+    n = lib().refk_pp_weight_sequence(_p(h), h.shape[0], float(hist_rate), _p(s), s.size, float(seq_rate),
+                                      float(acoustic_impedance), _p(out), s.size)
+    return out[:n]
+
+
+def pp_postprocessing(histogram, hist_rate, sequence, seq_rate, acoustic_impedance):
+    h, s = _pp_hist_seq(histogram, sequence)
+    out = np.zeros(s.size, np.float32)
+    n = lib().refk_pp_postprocessing(_p(h), h.shape[0], float(hist_rate), _p(s), s.size, float(seq_rate),
+                                     float(acoustic_impedance), _p(out), s.size)
+    return out[:n]
+
+
+def pp_multiband_mixdown(multiband, sample_rate):
+    m = np.ascontiguousarray(multiband, np.float32).reshape(-1, 8)
+    out = np.zeros(m.shape[0], np.float32)
+    lib().refk_pp_multiband_mixdown(_p(m), m.shape[0], float(sample_rate), _p(out))
+    return out
+
+
+def pp_band_params(sample_rate):
+    edges, wf = np.zeros(9, np.float64), np.zeros(1, np.float64)
+    lib().refk_pp_band_params(float(sample_rate), _p(edges), _p(wf))
+    return edges, float(wf[0])
+
+
+def pp_magnitudes(frequency, edge, edge_hi, width_factor, l=0):
+    """-> (lopass at edge, hipass at edge, bandpass over [edge, edge_hi])"""
+    out = np.zeros(3, np.float64)
+    lib().refk_pp_magnitudes(float(frequency), float(edge), float(edge_hi), float(width_factor), int(l), _p(out))
+    return tuple(out)
+
+
+def pp_crossover(lo, hi, cutoff, width):
+    a, b = np.ascontiguousarray(lo, np.float32), np.ascontiguousarray(hi, np.float32)
+    out = np.zeros(max(a.size, b.size, 1), np.float32)
+    n = lib().refk_pp_crossover(_p(a), a.size, _p(b), b.size, float(cutoff), float(width), _p(out))
+    return out[:n]
+
+
+def pp_left_hanning(length):
+    out = np.zeros(length, np.float32)
+    lib().refk_pp_left_hanning(length, _p(out))
+    return out
+
+
+def pp_fft_length(n):
+    return int(lib().refk_pp_fft_length(n))
