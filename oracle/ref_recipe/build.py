@@ -265,27 +265,30 @@ def function_source(rel: str, signature_regex: str) -> str:
     return text[m.start():j + 1]
 
 
-def host_voxel_program() -> str:
-    """The reference's HOST voxelisation code (not OpenCL): compiled unmodified behind the GLM
-    stand-in of hoststubs/ -- tri_cube_intersection.cpp and the headers ndim_tree.h,
-    voxel_collection.h, indexing.h, utilities/range.h as whole files (#included where they lie),
-    geo::overlaps of box.cpp:21-27 and get_flattened of voxel_collection.cpp:9-37 as single
-    functions (the rest of those two files needs geometric.h / scene_data.h)."""
-    core = os.path.join(REF, "src", "core")
-    overlaps = function_source("src/core/src/geo/box.cpp", r"bool overlaps\(const box& b, const triangle_vec3& t\)\s*\{")
-    flattened = function_source("src/core/src/spatial_division/voxel_collection.cpp",
-                                r"util::aligned::vector<cl_uint> get_flattened\(\s*const voxel_collection<3>& voxels\)\s*\{")
+def host_scene_program() -> str:
+    """The reference's HOST scene code, whole files #included where they lie behind the GLM stand-in:
+    the octree voxeliser (tri_cube_intersection.cpp, box.cpp, ndim_tree.h, voxel_collection.h/.cpp,
+    voxelised_scene_data.h), the CPU ray casts (geometric.cpp, triangle_vec.cpp, the voxel walk of
+    voxel_collection.cpp:41-124) and the image-source stage (raytracer/src/image_source/{tree,
+    postprocess_branches,exact}.cpp, pressure_intensity.cpp). exact.h prints its shell counts to
+    std::cout; nothing else is said or changed."""
+    src = os.path.join(REF, "src")
+    files = [
+        ("core", "src", "geo", "tri_cube_intersection.cpp"), ("core", "src", "geo", "triangle_vec.cpp"),
+        ("core", "src", "geo", "geometric.cpp"), ("core", "src", "geo", "box.cpp"),
+        ("core", "src", "spatial_division", "voxel_collection.cpp"), ("core", "src", "pressure_intensity.cpp"),
+        ("raytracer", "src", "image_source", "tree.cpp"), ("raytracer", "src", "image_source", "postprocess_branches.cpp"),
+        ("raytracer", "src", "image_source", "exact.cpp"),
+    ]
     return "\n".join([
         "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
-        "#include <array>", "#include <cmath>", "#include <functional>", "#include <memory>", "#include <numeric>",
-        "#include <stdexcept>", "#include <vector>",
-        '#include "glm/glm.hpp"',
-        '#include "core/geo/tri_cube_intersection.h"',
-        '#include "core/spatial_division/voxel_collection.h"',
-        '#include "%s"' % os.path.join(core, "src", "geo", "tri_cube_intersection.cpp"),
-        "namespace wayverb { namespace core { namespace geo {", overlaps, "} } }",
-        "namespace wayverb { namespace core {", flattened, "} }",
-        '#include "%s"' % os.path.join(HERE, "voxel_driver.inc"),
+        "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
+        "#include <future>", "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <random>",
+        "#include <stdexcept>", "#include <vector>", "#include <experimental/optional>",
+    ] + ['#include "%s"' % os.path.join(src, *f) for f in files] + [
+        '#include "raytracer/image_source/get_direct.h"',
+        '#include "raytracer/image_source/reflection_path_builder.h"',
+        '#include "%s"' % os.path.join(HERE, "scene_driver.inc"),
     ]) + "\n"
 
 
@@ -322,7 +325,7 @@ def host_pp_program() -> str:
     ]) + "\n"
 
 
-HOST_UNITS = {"ref_voxel.cpp": host_voxel_program, "ref_pp.cpp": host_pp_program}
+HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program}
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
                  "-I", os.path.join(REF, "src", "utilities", "include"),
                  "-I", os.path.join(REF, "src", "raytracer", "include"),
@@ -352,7 +355,8 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in os.listdir(HERE))
+    return any(os.path.getmtime(os.path.join(d, f)) > t for d, _, files in os.walk(HERE) for f in files
+               if not f.endswith(".pyc"))
 
 
 def build(force: bool = False) -> str | None:

@@ -1,15 +1,20 @@
 // oracle/ref_recipe/hoststubs/glm/glm.hpp -- TEST INFRASTRUCTURE ONLY.
 //
-// Stand-in for the handful of GLM 0.9.8.1 names the reference's HOST voxelisation code uses
-// (tri_cube_intersection.cpp, box.cpp:21-27, ndim_tree.h, voxel_collection.h/.cpp:9-37,
-// indexing.h, utilities/range.h), so that those files can be compiled here UNMODIFIED (GLM is
-// fetched at configure time by the reference, config/dependencies.cmake, and is not in this
-// image). Semantics follow GLM's generic (non-SIMD) code paths:
+// Stand-in for the handful of GLM 0.9.8.1 names the reference's HOST scene code uses
+// (tri_cube_intersection.cpp, box.cpp, geometric.cpp, triangle_vec.cpp, ndim_tree.h,
+// voxel_collection.h/.cpp, voxelised_scene_data.h, indexing.h, utilities/range.h, and the
+// image-source files raytracer/src/image_source/{tree,postprocess_branches,exact}.cpp), so that those
+// files can be compiled here UNMODIFIED (GLM is fetched at configure time by the reference,
+// config/dependencies.cmake, and is not in this image). Semantics follow GLM's generic (non-SIMD)
+// code paths:
 //   operators        componentwise
 //   dot(a, b)        tmp = a * b; tmp.x + tmp.y + tmp.z            (func_geometric.inl compute_dot)
 //   cross(x, y)      (x.y*y.z - y.y*x.z, x.z*y.x - y.z*x.x, x.x*y.y - y.x*x.y)
 //   normalize(v)     v * inversesqrt(dot(v, v)),  inversesqrt(x) = 1 / sqrt(x)
-//   mix(a, b, t)     a + t * (b - a)
+//   length(v)        sqrt(dot(v, v));  distance(a, b) = length(b - a)
+//   mix(a, b, t)     a + t * (b - a) for a float t;  componentwise select (t ? b : a) for a bool vector
+//   lessThan / lessThanEqual / equal / isnan     componentwise, to a bool vector; any / all fold it
+//   vec -> ivec      componentwise static_cast (truncation), ceil componentwise std::ceil
 //   min / max        (y < x) ? y : x  /  (x < y) ? y : x, componentwise
 // These are the only places where this file, and not the reference's source, decides arithmetic.
 #pragma once
@@ -31,6 +36,10 @@ struct tvec2 {
     constexpr tvec2(const V& v) : x(T(v.x)), y(T(v.y)) {}  // GLM_EXPLICIT is empty: vec3 -> vec2 truncates
     T& operator[](size_t i) { return i == 0 ? x : y; }
     constexpr const T& operator[](size_t i) const { return i == 0 ? x : y; }
+    tvec2& operator+=(const tvec2& o) { x += o.x; y += o.y; return *this; }
+    tvec2& operator-=(const tvec2& o) { x -= o.x; y -= o.y; return *this; }
+    tvec2& operator*=(const tvec2& o) { x *= o.x; y *= o.y; return *this; }
+    tvec2& operator/=(const tvec2& o) { x /= o.x; y /= o.y; return *this; }
 };
 
 template <typename T>
@@ -60,6 +69,7 @@ using vec3 = tvec3<float>;
 using uvec3 = tvec3<unsigned>;
 using ivec3 = tvec3<int>;
 using bvec3 = tvec3<bool>;
+using bvec2 = tvec2<bool>;
 
 #define GLM_STUB_BINOP(op)                                                                                     \
     template <typename T> constexpr tvec3<T> operator op(const tvec3<T>& a, const tvec3<T>& b) {               \
@@ -75,16 +85,26 @@ GLM_STUB_BINOP(+)
 GLM_STUB_BINOP(-)
 GLM_STUB_BINOP(*)
 GLM_STUB_BINOP(/)
+GLM_STUB_BINOP(%)
 GLM_STUB_BINOP(&)
 GLM_STUB_BINOP(<<)
 #undef GLM_STUB_BINOP
 template <typename T> constexpr tvec3<T> operator-(const tvec3<T>& a) { return tvec3<T>(-a.x, -a.y, -a.z); }
 template <typename T> constexpr bool operator==(const tvec3<T>& a, const tvec3<T>& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 template <typename T> constexpr bool operator!=(const tvec3<T>& a, const tvec3<T>& b) { return !(a == b); }
-template <typename T> constexpr tvec2<T> operator+(const tvec2<T>& a, const tvec2<T>& b) { return tvec2<T>(a.x + b.x, a.y + b.y); }
-template <typename T> constexpr tvec2<T> operator-(const tvec2<T>& a, const tvec2<T>& b) { return tvec2<T>(a.x - b.x, a.y - b.y); }
-template <typename T> constexpr tvec2<T> operator*(const tvec2<T>& a, const tvec2<T>& b) { return tvec2<T>(a.x * b.x, a.y * b.y); }
-template <typename T> constexpr tvec2<T> operator*(const tvec2<T>& a, T s) { return tvec2<T>(a.x * s, a.y * s); }
+#define GLM_STUB_BINOP2(op)                                                                                    \
+    template <typename T> constexpr tvec2<T> operator op(const tvec2<T>& a, const tvec2<T>& b) {               \
+        return tvec2<T>(a.x op b.x, a.y op b.y);                                                               \
+    }                                                                                                          \
+    template <typename T> constexpr tvec2<T> operator op(const tvec2<T>& a, T s) { return tvec2<T>(a.x op s, a.y op s); } \
+    template <typename T> constexpr tvec2<T> operator op(T s, const tvec2<T>& a) { return tvec2<T>(s op a.x, s op a.y); }
+GLM_STUB_BINOP2(+)
+GLM_STUB_BINOP2(-)
+GLM_STUB_BINOP2(*)
+GLM_STUB_BINOP2(/)
+#undef GLM_STUB_BINOP2
+template <typename T> constexpr bool operator==(const tvec2<T>& a, const tvec2<T>& b) { return a.x == b.x && a.y == b.y; }
+template <typename T> constexpr bool operator!=(const tvec2<T>& a, const tvec2<T>& b) { return !(a == b); }
 
 template <typename T> constexpr tvec3<T> min(const tvec3<T>& x, const tvec3<T>& y) {
     return tvec3<T>(y.x < x.x ? y.x : x.x, y.y < x.y ? y.y : x.y, y.z < x.z ? y.z : x.z);
@@ -107,8 +127,18 @@ inline vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }
 inline float length(const vec3& v) { return std::sqrt(dot(v, v)); }
 inline float distance(const vec3& a, const vec3& b) { return length(b - a); }
 inline vec3 mix(const vec3& a, const vec3& b, float t) { return a + t * (b - a); }
-inline bvec3 lessThan(const vec3& a, const vec3& b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
-inline bool any(const bvec3& v) { return v.x || v.y || v.z; }
-inline bool all(const bvec3& v) { return v.x && v.y && v.z; }
+inline vec3 ceil(const vec3& v) { return vec3(std::ceil(v.x), std::ceil(v.y), std::ceil(v.z)); }
+template <typename T> constexpr bvec3 lessThan(const tvec3<T>& a, const tvec3<T>& b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
+template <typename T> constexpr bvec3 lessThanEqual(const tvec3<T>& a, const tvec3<T>& b) { return bvec3(a.x <= b.x, a.y <= b.y, a.z <= b.z); }
+template <typename T> constexpr bvec3 equal(const tvec3<T>& a, const tvec3<T>& b) { return bvec3(a.x == b.x, a.y == b.y, a.z == b.z); }
+template <typename T> constexpr bvec2 lessThan(const tvec2<T>& a, const tvec2<T>& b) { return bvec2(a.x < b.x, a.y < b.y); }
+inline bvec3 isnan(const vec3& v) { return bvec3(std::isnan(v.x), std::isnan(v.y), std::isnan(v.z)); }
+template <typename T> constexpr tvec3<T> mix(const tvec3<T>& x, const tvec3<T>& y, const bvec3& a) {
+    return tvec3<T>(a.x ? y.x : x.x, a.y ? y.y : x.y, a.z ? y.z : x.z);
+}
+constexpr bool any(const bvec3& v) { return v.x || v.y || v.z; }
+constexpr bool all(const bvec3& v) { return v.x && v.y && v.z; }
+constexpr bool any(const bvec2& v) { return v.x || v.y; }
+constexpr bool all(const bvec2& v) { return v.x && v.y; }
 
 }  // namespace glm

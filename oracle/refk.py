@@ -109,6 +109,12 @@ def lib():
         L.refk_overlaps.restype = i
         L.refk_overlaps.argtypes = [vp, vp]
         d = C.c_double
+        L.refk_is_intersects.argtypes = [vp, sz, vp, sz, sz, f, vp, vp, vp, sz, vp, vp]
+        L.refk_is_mirror.argtypes = [vp, vp, vp]
+        L.refk_is_image_source.restype = sz
+        L.refk_is_image_source.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, vp, vp, sz, sz, sz, d, i, i, vp, sz]
+        L.refk_is_exact_shoebox.restype = sz
+        L.refk_is_exact_shoebox.argtypes = [vp, vp, vp, vp, f, d, d, vp, sz]
         L.refk_pp_rate_law.argtypes = [d, d, d, vp]
         L.refk_pp_intervals.argtypes = [u, sz, vp, vp]
         L.refk_pp_dirac_sequence.restype = sz
@@ -378,6 +384,62 @@ def overlaps(box6, tri9) -> bool:
     b = np.ascontiguousarray(box6, np.float32).reshape(6)
     t = np.ascontiguousarray(tri9, np.float32).reshape(9)
     return bool(lib().refk_overlaps(_p(b), _p(t)))
+
+
+# ---- image sources (HOST code of the reference: image_source/*.cpp, geometric.cpp, the CPU voxel walk) ----
+def _scene_arrays(sc):
+    v = np.ascontiguousarray(sc.vertices, np.float32).reshape(-1, 4)
+    t = np.ascontiguousarray(sc.triangles).view(np.uint32).reshape(-1, 4)
+    s = np.ascontiguousarray(sc.surfaces).view(np.float32).reshape(-1, 16)
+    return v, t, s
+
+
+def is_intersects(sc, origins, directions, ignore=None, depth=5, padding=0.1):
+    """intersects(voxelised, ray, to_ignore) (voxelised_scene_data.h:80-106) -> (t, triangle or 0xffffffff)"""
+    v, t, _ = _scene_arrays(sc)
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    dirs = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+    ig = None if ignore is None else np.ascontiguousarray(ignore, np.uint32)
+    ts, idx = np.zeros(o.shape[0], np.float32), np.zeros(o.shape[0], np.uint32)
+    lib().refk_is_intersects(_p(v), v.shape[0], _p(t), t.shape[0], int(depth), float(padding), _p(o), _p(dirs),
+                             None if ig is None else _p(ig), o.shape[0], _p(ts), _p(idx))
+    return ts, idx
+
+
+def is_mirror(tri9, point3):
+    """geo::mirror(point, triangle), geo::normal(triangle)"""
+    out = np.zeros(6, np.float32)
+    lib().refk_is_mirror(_p(np.ascontiguousarray(tri9, np.float32)), _p(np.ascontiguousarray(point3, np.float32)), _p(out))
+    return out[:3], out[3:]
+
+
+def is_image_source(sc, reflections, source, receiver, max_order, acoustic_impedance=400.0, flip_phase=False,
+                    with_direct=True, depth=5, padding=0.1):
+    """the image-source stage (reflection_processor/image_source.cpp:36-68) on reflection records
+    [steps][n_rays] -> impulses, in the reference's order"""
+    v, t, s = _scene_arrays(sc)
+    r = np.ascontiguousarray(reflections, REFL_DT)
+    steps, n = r.shape
+    src, rcv = np.asarray(source, np.float32), np.asarray(receiver, np.float32)
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, IMPULSE_DT)
+        cnt = lib().refk_is_image_source(_p(v), v.shape[0], _p(t), t.shape[0], _p(s), s.shape[0], int(depth),
+                                         float(padding), _p(src), _p(rcv), _p(r), steps, n, int(max_order),
+                                         float(acoustic_impedance), int(flip_phase), int(with_direct), _p(out), cap)
+        if cnt <= cap:
+            return out[:cnt]
+        cap = cnt
+
+
+def is_exact_shoebox(box_min, box_max, source, receiver, absorption, max_distance, acoustic_impedance=400.0):
+    a = [np.asarray(x, np.float32) for x in (box_min, box_max, source, receiver)]
+    cap = 1 << 16
+    out = np.zeros(cap, IMPULSE_DT)
+    n = lib().refk_is_exact_shoebox(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), float(absorption), float(max_distance),
+                                    float(acoustic_impedance), _p(out), cap)
+    assert n <= cap
+    return out[:n]
 
 
 # ---- post-processing (HOST code of the reference: stochastic/postprocessing.cpp, frequency_domain) ----

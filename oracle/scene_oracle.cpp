@@ -17,11 +17,12 @@
 //
 // Parity pinning: PINNED to reference-run output, with one stated caveat. The reference's host C++
 // needs GLM, which is fetched at configure time and is not in this image; oracle/ref_recipe/build.py
-// compiles the reference's OWN tri_cube_intersection.cpp, ndim_tree.h, voxel_collection.h, indexing.h,
-// utilities/range.h, geo::overlaps (box.cpp:21-27) and get_flattened (voxel_collection.cpp:9-37),
-// unmodified and where they lie, behind a stand-in for the GLM operations they use
-// (oracle/ref_recipe/hoststubs/glm/glm.hpp: componentwise operators, dot, cross, normalize, min/max
-// after GLM 0.9.8.1's generic code paths -- the only arithmetic that stand-in decides).
+// compiles the reference's OWN tri_cube_intersection.cpp, box.cpp, geometric.cpp, voxel_collection.cpp,
+// ndim_tree.h, voxel_collection.h, voxelised_scene_data.h (make_voxelised_scene_data as written),
+// indexing.h and utilities/range.h, whole, unmodified and where they lie, behind a stand-in for the
+// GLM operations they use (oracle/ref_recipe/hoststubs/glm/glm.hpp: componentwise operators, dot,
+// cross, normalize, min/max ... after GLM 0.9.8.1's generic code paths -- the only arithmetic that
+// stand-in decides).
 // tests/test_ref_pin_scene.py asserts that this file AND the product's wvb_voxelise reproduce that
 // build's flattened index entry for entry on the demo concert hall, its subdivided variants and
 // random triangle soups. On top: the reference's own property test (core/tests/voxel_tests.cpp:

@@ -1,7 +1,7 @@
 """Pins the scene-preparation oracle (oracle/scene_oracle.cpp) AND the product's voxeliser
 (wvb_voxelise) to the REFERENCE'S OWN host source: src/core/src/geo/tri_cube_intersection.cpp,
-geo::overlaps (box.cpp:21-27), ndim_tree.h, voxel_collection.h and get_flattened
-(voxel_collection.cpp:9-37), compiled unmodified from /root/reference into oracle/_ref behind a
+box.cpp, ndim_tree.h, voxel_collection.h/.cpp (get_flattened) and voxelised_scene_data.h
+(make_voxelised_scene_data), whole files compiled unmodified from /root/reference into oracle/_ref behind a
 stand-in for the GLM operations they use (oracle/ref_recipe/hoststubs/glm/glm.hpp -- the one
 place where this repository, not the reference, decides arithmetic: componentwise operators,
 dot, cross, normalize, min/max, written after GLM 0.9.8.1's generic code paths). Voxel for voxel,
