@@ -278,8 +278,14 @@ def host_scene_program() -> str:
         ("core", "src", "geo", "geometric.cpp"), ("core", "src", "geo", "box.cpp"),
         ("core", "src", "spatial_division", "voxel_collection.cpp"), ("core", "src", "pressure_intensity.cpp"),
         ("raytracer", "src", "image_source", "tree.cpp"), ("raytracer", "src", "image_source", "postprocess_branches.cpp"),
-        ("raytracer", "src", "image_source", "exact.cpp"),
+        ("raytracer", "src", "image_source", "exact.cpp"), ("core", "src", "az_el.cpp"),
     ]
+    sh = "src/raytracer/include/raytracer/reflection_processor/stochastic_histogram.h"
+    # the three binning pieces of stochastic_histogram.h:17-39 (the rest of that header runs the OpenCL finder)
+    sums = [function_source(sh, r"template <typename T, typename U, typename Alloc>\s*void energy_histogram_sum\("),
+            function_source(sh, r"template <typename T, typename U, typename Alloc, size_t Az, size_t El>\s*"
+                                r"void energy_histogram_sum\("),
+            function_source(sh, r"struct energy_histogram_sum_functor final \{") + ";"]
     return "\n".join([
         "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
         "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
@@ -288,6 +294,9 @@ def host_scene_program() -> str:
     ] + ['#include "%s"' % os.path.join(src, *f) for f in files] + [
         '#include "raytracer/image_source/get_direct.h"',
         '#include "raytracer/image_source/reflection_path_builder.h"',
+        '#include "raytracer/histogram.h"', '#include "raytracer/stochastic/postprocessing.h"',
+        '#include "core/vector_look_up_table.h"',
+        "namespace wayverb { namespace raytracer { namespace reflection_processor {"] + sums + ["} } }",
         '#include "%s"' % os.path.join(HERE, "scene_driver.inc"),
     ]) + "\n"
 

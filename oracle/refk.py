@@ -113,6 +113,9 @@ def lib():
         L.refk_is_mirror.argtypes = [vp, vp, vp]
         L.refk_is_image_source.restype = sz
         L.refk_is_image_source.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, vp, vp, sz, sz, sz, d, i, i, vp, sz]
+        L.refk_lut_index.argtypes = [vp, sz, vp, vp]
+        L.refk_histogram.restype = sz
+        L.refk_histogram.argtypes = [vp, vp, vp, sz, vp, d, d, i, vp, sz]
         L.refk_is_exact_shoebox.restype = sz
         L.refk_is_exact_shoebox.argtypes = [vp, vp, vp, vp, f, d, d, vp, sz]
         L.refk_pp_rate_law.argtypes = [d, d, d, vp]
@@ -323,6 +326,39 @@ def histogram_from_steps(steps, n_bins, speed_of_sound=340.0, histogram_rate=100
             dropped += int((~ok).sum())
             np.add.at(hist, b[ok], live["volume"][ok].astype(np.float64))
     return hist, dropped
+
+
+def reference_histogram(steps, receiver, speed_of_sound=340.0, histogram_rate=1000.0, specular_from_step=0,
+                        directional=False):
+    """The same through the reference's OWN host code -- incremental_histogram (raytracer/histogram.h:62-81)
+    with energy_histogram_sum_functor (stochastic_histogram.h:17-39) and, for the directional case,
+    vector_look_up_table<..., 20, 9>::index -- on the impulses in the order the group processor pushes them
+    (stochastic first, then specular, step by step): float bins, summed in that order.
+    -> float32 [bins, 8] or [20, 9, bins, 8]."""
+    vols, poss, dists = [], [], []
+    for step, _refl, sto, hit in steps:
+        for g in [sto] + ([hit] if step >= specular_from_step else []):
+            live = g[g["distance"] != 0]                                      # finder.h:65-76
+            vols.append(live["volume"])
+            poss.append(live["position"][:, :3])
+            dists.append(live["distance"])
+    v = np.ascontiguousarray(np.concatenate(vols), np.float32)
+    p = np.ascontiguousarray(np.concatenate(poss), np.float32)
+    dd = np.ascontiguousarray(np.concatenate(dists), np.float32)
+    rcv = np.asarray(receiver, np.float32)
+    args = (_p(v), _p(p), _p(dd), dd.size, _p(rcv), float(speed_of_sound), float(histogram_rate), int(directional))
+    bins = lib().refk_histogram(*args, None, 0)
+    out = np.zeros((20, 9, bins, 8) if directional else (bins, 8), np.float32)
+    lib().refk_histogram(*args, _p(out), bins)
+    return out
+
+
+def lut_index(v):
+    """vector_look_up_table<T, 20, 9>::index for unit vectors [n, 3] -> (azimuth cell, elevation cell)"""
+    v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)
+    az, el = np.zeros(v.shape[0], np.int32), np.zeros(v.shape[0], np.int32)
+    lib().refk_lut_index(_p(v), v.shape[0], _p(az), _p(el))
+    return az, el
 
 
 # ---- mesh setup ----------------------------------------------------------------------------------

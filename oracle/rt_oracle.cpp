@@ -506,16 +506,19 @@ inline bool segment_sphere(f3 p1, f3 p2, f3 sc, float r) {
 // compute_azimuth_elevation (az_el.cpp:53-68) + azimuth/elevation_to_index
 // (vector_look_up_table.h:53-77,112-116). Host code in the reference: libm
 // atan2f/asinf on float, the rest in double.
+// core::degrees (vector_look_up_table.h:22): `radians * 180 / M_PI` on a float, returned as float --
+// the product is rounded to float, the quotient is taken in double and rounded to float again
+inline float degrees_f(float radians) { return float(double(radians * 180) / M_PI); }
+
 inline void lut_index(f3 v, int* az_cell, int* el_cell) {
     float az = std::atan2(v.x, -v.z);
     const float el = std::asin(v.y);
     if (almost_equal(el, float(-M_PI / 2), 10) || almost_equal(el, float(M_PI / 2), 10)) az = 0;
-    const double deg = 180.0 / M_PI;
-    double a = double(-az) * deg;
+    double a = degrees_f(-az);
     a += (360.0 / 20) / 2;
     while (a < 0) a += 360;
     *az_cell = int(size_t(a / (360.0 / 20)) % 20);
-    double e = double(el) * deg;
+    double e = degrees_f(el);
     e += 90 + (180.0 / 10) / 2;
     while (e < 0) e += 360;
     size_t adj = size_t(e / (180.0 / 10)) % 20;

@@ -10,7 +10,15 @@ stream, sin / cos / normalize / dot rounding -- is supplied identically to both 
 (DESIGN.md "Precision").
 
 Asserted: reflection records of EVERY step bit-identical; the energy histogram equal to 1e-12
-of its peak (the two sides add the same fp32 impulses into fp64 bins in different orders)."""
+of its peak (the two sides add the same fp32 impulses into fp64 bins in different orders).
+
+The host binning itself is then taken from the reference too: incremental_histogram
+(raytracer/histogram.h:62-81), energy_histogram_sum_functor (stochastic_histogram.h:17-39) and
+vector_look_up_table<..., 20, 9>::index with core/src/az_el.cpp, compiled as they are
+(refk.reference_histogram, refk.lut_index). The reference sums float bands in impulse order, the
+product and the oracle sum the same floats in double: same bins hit, same directional cells, and
+values within float accumulation error (2e-5 of the peak) -- the one stated precision difference of
+the histogram (DESIGN.md "Precision")."""
 import numpy as np
 import pytest
 
@@ -47,7 +55,52 @@ def run_pair(sc, n, depth, seed, specular_from_step=0, radius=0.1):
     assert got_drop == want_drop
     assert want_h.max() > 0
     assert np.abs(got_h - want_h).max() <= 1e-12 * want_h.max()
+    # the reference's own float histogram of the same impulses (it grows as needed: rows beyond
+    # n_bins are what the fixed-size side counts as dropped)
+    ref_h = refk.reference_histogram(steps, RCV, specular_from_step=specular_from_step)
+    rows = min(n_bins, ref_h.shape[0])
+    padded = np.zeros((n_bins, 8))
+    padded[:rows] = ref_h[:rows]
+    assert np.array_equal(padded != 0, want_h != 0)
+    assert np.abs(padded - want_h).max() <= 2e-5 * want_h.max()
+    assert (want_drop == 0) == (ref_h.shape[0] <= n_bins)
     return want_r, want_h
+
+
+def test_directional_histogram_cells_are_the_references():
+    """directional_energy_histogram<20, 9>: every impulse lands in the reference's cell"""
+    sc = scene.box_scene((4.0, 3.0, 6.0), subdiv=2, side=8, surfaces=[scene.make_surface(0.1, 0.3)])
+    n, depth, seed, n_bins = 3000, 10, 17, 400
+    o, r = rto.Scene(sc), refk.RayScene(sc)
+    dirs = rto.directions(seed, n)
+    want_h, _, _ = o.trace(dirs, SRC, RCV, depth, seed=seed, n_bins=n_bins, directional=True)
+    energy = rto.ray_energy(n, SRC, RCV, 0.1)
+    steps = list(r.trace_steps(dirs, SRC, RCV, depth, lambda s: rto.step_rng(seed, n, s), initial_energy=energy))
+    ref_h = refk.reference_histogram(steps, RCV, directional=True)
+    rows = min(n_bins, ref_h.shape[2])
+    padded = np.zeros_like(want_h)
+    padded[:, :, :rows] = ref_h[:, :, :rows]
+    assert (want_h != 0).sum() > 5000 and (want_h.sum((2, 3)) != 0).sum() > 100      # many cells in use
+    assert np.array_equal(padded != 0, want_h != 0)
+    assert np.abs(padded - want_h).max() <= 2e-5 * want_h.max()
+
+
+def test_lut_index_is_the_references():
+    rng = np.random.default_rng(23)
+    v = rng.standard_normal((200000, 3))
+    v = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    special = np.array([[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1],
+                        [0, 0.99999994, 0.0003], [1e-8, -1, 0], [0.70710677, 0, 0.70710677],
+                        [-0.70710677, 0, -0.70710677], [0.15643446, 0, -0.98768836]], np.float32)
+    # cell borders: azimuth multiples of 9 degrees off the 18-degree grid, elevation multiples of 9
+    az = np.radians(np.arange(-180, 181, 9, dtype=np.float64))
+    el = np.radians(np.arange(-81, 90, 9, dtype=np.float64))
+    grid = np.array([[np.sin(-a) * np.cos(e), np.sin(e), -np.cos(-a) * np.cos(e)] for a in az for e in el], np.float32)
+    for pts in (v, special, grid):
+        a_r, e_r = refk.lut_index(pts)
+        a_o, e_o = rto.lut_index(pts)
+        assert np.array_equal(a_r, a_o) and np.array_equal(e_r, e_o)
+        assert a_r.min() >= 0 and a_r.max() <= 19 and e_r.min() >= 0 and e_r.max() <= 8
 
 
 @pytest.mark.parametrize("outward", [True, False])
