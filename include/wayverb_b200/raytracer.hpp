@@ -103,11 +103,9 @@ inline size_t compute_optimum_reflection_number(const core::flattened_scene& sce
     bool any = false;
     for (size_t i = 0; i != used.size(); ++i) {
         if (!used[i]) continue;
-        // min_absorption(surface) is min_element of the band vector, which the
-        // reference resolves to the FIRST band (min_element(float x) overload is
-        // never reached for a vector; it takes t.absorption as a whole and the
-        // double overload converts s0) -- we take the smallest band, the
-        // conservative reading
+        // min_absorption(surface) = min_element(surface.absorption): argument-dependent lookup takes the
+        // global min_element of core/cl/traits.h for the band vector, i.e. the smallest band
+        // (held against the reference's own header in tests/cpp/test_hostmath_pin.cpp)
         double m = scene.surfaces[i].absorption.s[0];
         for (float a : scene.surfaces[i].absorption.s) m = std::min<double>(m, a);
         min_abs = any ? std::min(min_abs, m) : m;

@@ -124,8 +124,8 @@ def yulewalk(na, ff, aa, npt=512):
     return B, A
 
 
-def arbitrary_magnitude_filter(freq, amp, order=ORDER):
-    """arbitrary_magnitude_filter.h:63-95: points (frequency 0..1 = dc..nyquist, amplitude)"""
+def envelope_grid(freq, amp):
+    """arbitrary_magnitude_filter.h:63-84: the 256 (frequency, magnitude) points handed to yulewalk"""
     pts = []
 
     def insert(p):  # frequency_domain_envelope::insert: lower_bound => BEFORE equal frequencies
@@ -157,6 +157,12 @@ def arbitrary_magnitude_filter(freq, amp, order=ORDER):
 
     f = [i / 255.0 for i in range(256)]
     m = [interp(v) for v in f]
+    return f, m
+
+
+def arbitrary_magnitude_filter(freq, amp, order=ORDER):
+    """arbitrary_magnitude_filter.h:63-95: points (frequency 0..1 = dc..nyquist, amplitude)"""
+    f, m = envelope_grid(freq, amp)
     return yulewalk(order, f, m)
 
 

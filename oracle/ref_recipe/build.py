@@ -301,6 +301,32 @@ def host_scene_program() -> str:
     ]) + "\n"
 
 
+def host_math_program() -> str:
+    """The reference's small closed-form HOST functions that the product's host side restates: whole
+    files where they compile (mesh_descriptor.cpp, config.cpp, frequency_domain_envelope.cpp, filters.cpp,
+    fitted_boundary.h & co. over an IT++ stand-in that forwards the fit), two functions of the OpenCL-bound
+    stochastic/finder.{h,cpp} taken singly."""
+    src = os.path.join(REF, "src")
+    wg = os.path.join(src, "waveguide", "src")
+    energy_h = function_source("src/raytracer/include/raytracer/stochastic/finder.h",
+                               r"constexpr auto compute_ray_energy\(size_t total_rays,\s*float dist,\s*float open_angle\)\s*\{")
+    energy_cpp = function_source("src/raytracer/src/stochastic/finder.cpp",
+                                 r"float compute_ray_energy\(size_t total_rays,\s*const glm::vec3& source,")
+    return "\n".join([
+        "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+        "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
+        "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <stdexcept>", "#include <vector>",
+        '#include "%s"' % os.path.join(wg, "mesh_descriptor.cpp"),
+        '#include "%s"' % os.path.join(wg, "config.cpp"),
+        '#include "%s"' % os.path.join(wg, "frequency_domain_envelope.cpp"),
+        '#include "%s"' % os.path.join(wg, "filters.cpp"),
+        '#include "waveguide/fitted_boundary.h"', '#include "waveguide/calibration.h"',
+        '#include "raytracer/optimum_reflection_number.h"', '#include "core/cl/scene_structs.h"',
+        "namespace wayverb { namespace raytracer { namespace stochastic {", energy_h, energy_cpp, "} } }",
+        '#include "%s"' % os.path.join(HERE, "hostmath_driver.inc"),
+    ]) + "\n"
+
+
 def host_pp_program() -> str:
     """The reference's HOST post-processing code: raytracer/src/stochastic/postprocessing.cpp and the
     whole frequency_domain library as files (#included where they lie) over the FFTW stand-in of
@@ -334,12 +360,13 @@ def host_pp_program() -> str:
     ]) + "\n"
 
 
-HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program}
+HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program}
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
                  "-I", os.path.join(REF, "src", "utilities", "include"),
                  "-I", os.path.join(REF, "src", "raytracer", "include"),
                  "-I", os.path.join(REF, "src", "frequency_domain", "include"),
-                 "-I", os.path.join(REF, "src", "hrtf", "lib", "include")]
+                 "-I", os.path.join(REF, "src", "hrtf", "lib", "include"),
+                 "-I", os.path.join(REF, "src", "waveguide", "include")]
 
 UNITS = {
     "ref_wg_f32.cpp": lambda: waveguide_program(False),

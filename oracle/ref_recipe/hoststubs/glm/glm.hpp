@@ -14,7 +14,8 @@
 //   length(v)        sqrt(dot(v, v));  distance(a, b) = length(b - a)
 //   mix(a, b, t)     a + t * (b - a) for a float t;  componentwise select (t ? b : a) for a bool vector
 //   lessThan / lessThanEqual / equal / isnan     componentwise, to a bool vector; any / all fold it
-//   vec -> ivec      componentwise static_cast (truncation), ceil componentwise std::ceil
+//   vec -> ivec      componentwise static_cast (truncation), ceil / round componentwise std::ceil /
+//                    std::round (GLM_HAS_CXX11_STL: func_common.inl takes ::std::round)
 //   min / max        (y < x) ? y : x  /  (x < y) ? y : x, componentwise
 // These are the only places where this file, and not the reference's source, decides arithmetic.
 #pragma once
@@ -127,6 +128,7 @@ inline vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }
 inline float length(const vec3& v) { return std::sqrt(dot(v, v)); }
 inline float distance(const vec3& a, const vec3& b) { return length(b - a); }
 inline vec3 mix(const vec3& a, const vec3& b, float t) { return a + t * (b - a); }
+inline vec3 round(const vec3& v) { return vec3(std::round(v.x), std::round(v.y), std::round(v.z)); }
 inline vec3 ceil(const vec3& v) { return vec3(std::ceil(v.x), std::ceil(v.y), std::ceil(v.z)); }
 template <typename T> constexpr bvec3 lessThan(const tvec3<T>& a, const tvec3<T>& b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
 template <typename T> constexpr bvec3 lessThanEqual(const tvec3<T>& a, const tvec3<T>& b) { return bvec3(a.x <= b.x, a.y <= b.y, a.z <= b.z); }

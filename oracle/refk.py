@@ -32,6 +32,9 @@ IMPULSE_DT = np.dtype([("volume", "<f4", (8,)), ("position", "<f4", (4,)), ("dis
                        ("pad", "<f4", (3,))])
 
 _lib = None
+# (order, points, f[points], m[points], b_out[order + 1], a_out[order + 1]) -- hoststubs/itpp/signal/filter_design.h
+YULEWALK_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                          C.POINTER(C.c_double), C.POINTER(C.c_double))
 
 
 def available() -> bool:
@@ -113,6 +116,21 @@ def lib():
         L.refk_is_mirror.argtypes = [vp, vp, vp]
         L.refk_is_image_source.restype = sz
         L.refk_is_image_source.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, vp, vp, sz, sz, sz, d, i, i, vp, sz]
+        L.refk_hm_to_impedance.argtypes = [vp, vp, vp, vp]
+        L.refk_hm_to_flat.argtypes = [d, vp, vp]
+        L.refk_hm_is_stable.restype = i
+        L.refk_hm_is_stable.argtypes = [vp]
+        L.refk_hm_peak_biquad.argtypes = [d, d, d, vp]
+        L.refk_hm_convolve3.argtypes = [vp, vp, vp]
+        L.refk_hm_reflectance_filter.restype = i
+        L.refk_hm_reflectance_filter.argtypes = [vp, d, YULEWALK_CB, vp, vp, vp]
+        L.refk_hm_reflection_number.restype = sz
+        L.refk_hm_reflection_number.argtypes = [d]
+        L.refk_hm_ray_energy.restype = f
+        L.refk_hm_ray_energy.argtypes = [sz, vp, vp, f]
+        L.refk_hm_rates.argtypes = [f, d, vp]
+        L.refk_hm_calibration_factor.restype = d
+        L.refk_hm_calibration_factor.argtypes = [f, d]
         L.refk_lut_index.argtypes = [vp, sz, vp, vp]
         L.refk_histogram.restype = sz
         L.refk_histogram.argtypes = [vp, vp, vp, sz, vp, d, d, i, vp, sz]
@@ -558,3 +576,64 @@ def pp_left_hanning(length):
 
 def pp_fft_length(n):
     return int(lib().refk_pp_fft_length(n))
+
+
+# ---- closed-form host functions (waveguide/fitted_boundary.h, filters.cpp, stable.h, ...) --------------
+def hm_to_impedance(b, a):
+    b, a = np.ascontiguousarray(b, np.float64), np.ascontiguousarray(a, np.float64)
+    ob, oa = np.zeros(7), np.zeros(7)
+    lib().refk_hm_to_impedance(_p(b), _p(a), _p(ob), _p(oa))
+    return ob, oa
+
+
+def hm_to_flat(absorption):
+    ob, oa = np.zeros(7), np.zeros(7)
+    lib().refk_hm_to_flat(float(absorption), _p(ob), _p(oa))
+    return ob, oa
+
+
+def hm_is_stable(a) -> bool:
+    return bool(lib().refk_hm_is_stable(_p(np.ascontiguousarray(a, np.float64))))
+
+
+def hm_peak_biquad(gain, centre, q):
+    out = np.zeros(6)
+    lib().refk_hm_peak_biquad(float(gain), float(centre), float(q), _p(out))
+    return out[:3], out[3:]
+
+
+def hm_convolve3(biquads):
+    c = np.ascontiguousarray(biquads, np.float64).reshape(18)
+    ob, oa = np.zeros(7), np.zeros(7)
+    lib().refk_hm_convolve3(_p(c), _p(ob), _p(oa))
+    return ob, oa
+
+
+def hm_reflectance_filter(absorption, sample_rate, fit):
+    """compute_reflectance_filter_coefficients (fitted_boundary.h:79-104) as the reference wrote it, the
+    Yule-Walker fit itself supplied by `fit(order, f, m) -> (b, a)` (IT++ is not in the image).
+    -> (b, a, f256, m256, threw)"""
+    def cb(order, n, f, m, b_out, a_out):
+        b, a = fit(order, np.array(f[:n]), np.array(m[:n]))
+        for k in range(order + 1):
+            b_out[k], a_out[k] = float(b[k]), float(a[k])
+    ab = np.ascontiguousarray(absorption, np.float64)
+    ob, oa, grid = np.zeros(7), np.zeros(7), np.zeros(512)
+    threw = lib().refk_hm_reflectance_filter(_p(ab), float(sample_rate), YULEWALK_CB(cb), _p(ob), _p(oa), _p(grid))
+    return ob, oa, grid[:256], grid[256:], bool(threw)
+
+
+def hm_reflection_number(min_absorption) -> int:
+    return int(lib().refk_hm_reflection_number(float(min_absorption)))
+
+
+def hm_ray_energy(total_rays, source, receiver, radius) -> float:
+    s, r = np.asarray(source, np.float32), np.asarray(receiver, np.float32)
+    return float(lib().refk_hm_ray_energy(int(total_rays), _p(s), _p(r), float(radius)))
+
+
+def hm_rates(spacing, speed_of_sound):
+    """-> (compute_sample_rate, config::time_step, config::grid_spacing(c, dt), config::speed_of_sound(dt, h))"""
+    out = np.zeros(4)
+    lib().refk_hm_rates(float(spacing), float(speed_of_sound), _p(out))
+    return tuple(out)
