@@ -129,3 +129,56 @@ def test_load_obj_builds_the_engine_defaults(tmp_path):
     assert np.allclose(sc.aabb, [-0.1, -0.1, -0.1, 4.1, 3.1, 6.1])      # padded by 0.1
     _, want = sco.voxelise(sc.vertices, sc.triangles, 5, 0.1)
     assert np.array_equal(sc.voxel_index, want)
+
+
+def test_obj_reader_survives_damaged_files():
+    """Whatever bytes arrive, wvb_obj_parse either refuses (WvbError) or returns triangles whose vertex
+    and material indices are in range -- never a crash, never an index the ray kernels would follow
+    out of the arrays. Hand-written corner cases, then 600 random mutations of the concert hall."""
+    import random
+    rnd = random.Random(7)
+    accepted = refused = 0
+
+    def parse(text):
+        nonlocal accepted, refused
+        try:
+            v, t, names = scene.parse_obj(text)
+        except _lib.WvbError:
+            refused += 1
+            return
+        accepted += 1
+        if t.size:
+            assert max(t["v0"].max(), t["v1"].max(), t["v2"].max()) < v.shape[0]
+            assert t["surface"].max() < max(len(names), 1)
+
+    tri = "v 0 0 0\nv 1 0 0\nv 0 1 0\n"
+    for text in ["", "\n", "v", "v 1", "v 1 2", "f 1 2 3", tri + "f -1 -2 -3", tri + "f 1 2 99999999999999999999",
+                 tri + "f 1/1/1 2//2 3/3", tri + "f 1 2", "v nan inf -inf\nv 1e999 1 1\nv 1 1 1\nf 1 2 3",
+                 "usemtl\nusemtl a\nusemtl a\n" + tri + "f 1 2 3 1 2 3 1 2 3", "f 0 0 0", tri + "f 0 1 2", "f / / /",
+                 "f 1/ 2/ 3/", "v 1 2 3 4 5 6 7\n", "v\t1\t2\t3\r\nv 1 2 3\r\nv 3 2 1\r\nf 1 2 3\r\n", "\x00\x00v 1 2 3",
+                 "v 0 0 0\n" * 5 + "f " + " ".join(str(i % 5 + 1) for i in range(10000)), "f " + "1" * 5000,
+                 "v " + "9" * 5000 + " 1 1", "usemtl " + "x" * 100000, tri + "f 4294967297 2 3",
+                 tri + "f -4294967297 2 3"]:
+        parse(text)
+    lines = open(scene.CONCERT_OBJ).read().splitlines()
+    words = ["1", "-1", "0", "99999", "1/2/3", "a", "1e400", "-", "//", "4294967296", "-4294967297"]
+    for _ in range(600):
+        ls = list(lines)
+        for _ in range(rnd.randint(1, 8)):
+            i = rnd.randrange(len(ls))
+            r = rnd.random()
+            if r < 0.2:
+                del ls[i]
+            elif r < 0.4:
+                ls[i] = ls[i][:rnd.randrange(len(ls[i]) + 1)]
+            elif r < 0.6:
+                ls[i] = rnd.choice(["v", "f", "vt", "vn", "usemtl", "g", "#", "l"]) + " " + \
+                    " ".join(rnd.choice(words) for _ in range(rnd.randint(0, 6)))
+            elif r < 0.8 and ls[i]:
+                b = bytearray(ls[i].encode("latin1"))
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+                ls[i] = b.decode("latin1")
+            else:
+                ls.insert(i, ls[rnd.randrange(len(ls))])
+        parse("\n".join(ls).encode("latin1"))
+    assert accepted > 50 and refused > 50

@@ -57,7 +57,7 @@ def parse_obj(text):
     t = np.zeros(nt.value, TRI_DT)
     names = C.create_string_buffer(max(nn.value, 1))
     check(lib().wvb_obj_parse(raw, len(raw), ptr(v), C.byref(nv), ptr(t), C.byref(nt), names, C.byref(nn)))
-    return v, t, names.raw[:nn.value].decode().split("\n")[:-1]
+    return v, t, names.raw[:nn.value].decode("utf-8", "replace").split("\n")[:-1]
 
 
 class Scene:
