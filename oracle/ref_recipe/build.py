@@ -327,6 +327,32 @@ def host_math_program() -> str:
     ]) + "\n"
 
 
+def host_run_program() -> str:
+    """The reference's waveguide HOST loop -- the waveguide::run template, program.cpp's class, setup.cpp,
+    the stock processors -- whole files #included where they lie over the host-memory cl.hpp stand-in
+    (hostcl/). From mesh.cpp only the constructor and the two getters are taken (the rest of that file
+    builds meshes with further OpenCL programs)."""
+    src = os.path.join(REF, "src")
+    wg = os.path.join(src, "waveguide", "src")
+    M = "src/waveguide/src/mesh.cpp"
+    mesh_members = [function_source(M, r"mesh::mesh\(mesh_descriptor descriptor, vectors vectors\)"),
+                    function_source(M, r"const mesh_descriptor& mesh::get_descriptor\(\) const "),
+                    function_source(M, r"const vectors& mesh::get_structure\(\) const ")]
+    files = [("cl", "filter_structs.cpp"), ("cl", "filters.cpp"), ("cl", "utils.cpp"), ("program.cpp",), ("setup.cpp",),
+             ("postprocessor", "node.cpp"), ("postprocessor", "directional_receiver.cpp"),
+             ("preprocessor", "gaussian.cpp")]
+    return "\n".join([
+        "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+        "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
+        "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <stdexcept>", "#include <vector>",
+    ] + ['#include "%s"' % os.path.join(wg, *f) for f in files] + [
+        '#include "waveguide/waveguide.h"', '#include "waveguide/preprocessor/hard_source.h"',
+        '#include "waveguide/preprocessor/soft_source.h"', '#include "core/callback_accumulator.h"',
+        "namespace wayverb { namespace waveguide {"] + mesh_members + ["} }",
+        '#include "%s"' % os.path.join(HERE, "hostrun_driver.inc"),
+    ]) + "\n"
+
+
 def host_pp_program() -> str:
     """The reference's HOST post-processing code: raytracer/src/stochastic/postprocessing.cpp and the
     whole frequency_domain library as files (#included where they lie) over the FFTW stand-in of
@@ -360,7 +386,8 @@ def host_pp_program() -> str:
     ]) + "\n"
 
 
-HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program}
+HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program, "ref_hostrun.cpp": host_run_program}
+HOSTCL_UNITS = {"ref_hostrun.cpp"}     # compiled with hostcl/ (the cl.hpp stand-in) in front
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
                  "-I", os.path.join(REF, "src", "utilities", "include"),
                  "-I", os.path.join(REF, "src", "raytracer", "include"),
@@ -419,7 +446,8 @@ def build(force: bool = False) -> str | None:
             f.write(make())
         obj = path[:-4] + ".o"
         flags = ["-std=gnu++14", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"]
-        r = subprocess.run([CXX] + flags + HOST_INCLUDES + ["-c", path, "-o", obj], capture_output=True, text=True)
+        first = ["-I", os.path.join(HERE, "hostcl")] if fname in HOSTCL_UNITS else []
+        r = subprocess.run([CXX] + flags + first + HOST_INCLUDES + ["-c", path, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ failed on %s:\n%s" % (path, r.stderr[-6000:]))
         objs.append(obj)

@@ -69,6 +69,7 @@ using ivec2 = tvec2<int>;
 using vec3 = tvec3<float>;
 using uvec3 = tvec3<unsigned>;
 using ivec3 = tvec3<int>;
+using dvec3 = tvec3<double>;
 using bvec3 = tvec3<bool>;
 using bvec2 = tvec2<bool>;
 

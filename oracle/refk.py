@@ -4,10 +4,13 @@ from /root/reference at build time and compiled for the host by oracle/ref_recip
 TEST INFRASTRUCTURE ONLY (tests/ and bench.py's reference arm). It exists to pin the oracle
 (oracle/wg_oracle.cpp, oracle/rt_oracle.cpp) to reference-run output; the product never loads it.
 
-Host loops of the reference that are C++ templates over OpenCL handles (waveguide.h:36-126,
-reflector.cpp:31-51, stochastic/finder.h:48-79, stochastic_histogram.h:70-111) cannot be
-compiled here; they are driven from this file in the order the reference drives them, each
-step citing its line.
+The reference's HOST code is in the same library, compiled where it lies behind stand-ins for the
+dependencies this image lacks (ref_recipe/hoststubs: GLM, FFTW, IT++, libsamplerate; ref_recipe/hostcl: a
+host-memory cl.hpp): the octree voxeliser, the image-source stage, histogram binning, post-processing,
+the filter-design pipeline, the mesh-descriptor maths, and the waveguide::run template itself with its
+stock processors (run_waveguide below, enqueueing the kernel above). Sim / RayScene.trace_steps drive the
+kernels step by step from Python in the reference's order for the tests that need to look between steps
+(waveguide.h:36-126, reflector.cpp:31-51, stochastic/finder.h:48-79), each step citing its line.
 """
 from __future__ import annotations
 
@@ -116,6 +119,9 @@ def lib():
         L.refk_is_mirror.argtypes = [vp, vp, vp]
         L.refk_is_image_source.restype = sz
         L.refk_is_image_source.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, vp, vp, sz, sz, sz, d, i, i, vp, sz]
+        L.refk_run_waveguide.restype = i
+        L.refk_run_waveguide.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i, sz, vp, sz, vp, vp, sz, vp,
+                                         sz, d, d, vp, vp, C.c_char_p, sz]
         L.refk_hm_to_impedance.argtypes = [vp, vp, vp, vp]
         L.refk_hm_to_flat.argtypes = [d, vp, vp]
         L.refk_hm_is_stable.restype = i
@@ -637,3 +643,43 @@ def hm_rates(spacing, speed_of_sound):
     out = np.zeros(4)
     lib().refk_hm_rates(float(spacing), float(speed_of_sound), _p(out))
     return tuple(out)
+
+
+# ---- the reference's own waveguide::run template, compiled for the host -----------------------------
+def run_waveguide(mesh, source_node=0, signal=(), receivers=(), soft=False, gaussian=None, directional=None,
+                  min_corner=(0.0, 0.0, 0.0), spacing=1.0):
+    """waveguide::run (waveguide.h:36-126) with the reference's stock processors, all compiled unmodified
+    over a host-memory cl.hpp stand-in and enqueueing the reference's kernel as compiled for the host.
+      source: hard_source (default) / soft_source (soft=True) fed `signal` at `source_node`, or
+              gaussian=(centre xyz, sdev, steps): preprocessor::gaussian
+      receivers: node indices read by postprocessor::node under callback_accumulator
+      directional=(node, sample_rate, ambient_density): a postprocessor::directional_receiver as well
+    -> (steps completed, pressures float32 [steps, receivers], directional float32 [steps, 4] or None)
+    raises RuntimeError with the reference's exception text."""
+    mc = np.asarray(min_corner, np.float32)
+    dims = np.asarray(mesh.dims, np.int32)
+    nodes = np.ascontiguousarray(mesh.nodes, NODE_DT)
+    coeffs = np.ascontiguousarray(mesh.coeffs, COEFF_DT)
+    b1 = np.ascontiguousarray(mesh.b1, np.uint32).reshape(-1, 1)
+    b2 = np.ascontiguousarray(mesh.b2, np.uint32).reshape(-1, 2)
+    b3 = np.ascontiguousarray(mesh.b3, np.uint32).reshape(-1, 3)
+    sig = np.ascontiguousarray(signal, np.float32)
+    steps = sig.size
+    g4 = np.zeros(4, np.float32)
+    kind = 1 if soft else 0
+    if gaussian is not None:
+        centre, sdev, steps = gaussian
+        g4[:3], g4[3], kind = centre, sdev, 2
+    rcv = np.ascontiguousarray(receivers, np.uint64)
+    out = np.zeros((steps, rcv.size), np.float32)
+    dnode, rate, density = (directional if directional is not None else (0xFFFFFFFFFFFFFFFF, 0.0, 0.0))
+    dout = np.zeros((steps, 4), np.float32)
+    done = C.c_size_t(0)
+    err = C.create_string_buffer(512)
+    status = lib().refk_run_waveguide(_p(mc), _p(dims), float(spacing), _p(nodes), nodes.size, _p(coeffs), coeffs.size,
+                                      _p(b1), b1.shape[0], _p(b2), b2.shape[0], _p(b3), b3.shape[0], kind,
+                                      int(source_node), _p(sig), int(steps), _p(g4), _p(rcv), rcv.size, _p(out),
+                                      int(dnode), float(rate), float(density), _p(dout), C.byref(done), err, 512)
+    if status:
+        raise RuntimeError(err.value.decode())
+    return done.value, out[:done.value], (dout[:done.value] if directional is not None else None)
