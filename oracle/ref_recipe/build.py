@@ -337,7 +337,9 @@ def host_run_program() -> str:
     M = "src/waveguide/src/mesh.cpp"
     mesh_members = [function_source(M, r"mesh::mesh\(mesh_descriptor descriptor, vectors vectors\)"),
                     function_source(M, r"const mesh_descriptor& mesh::get_descriptor\(\) const "),
-                    function_source(M, r"const vectors& mesh::get_structure\(\) const ")]
+                    function_source(M, r"const vectors& mesh::get_structure\(\) const "),
+                    function_source(M, r"void mesh::set_coefficients\(coefficients_canonical coefficients\)"),
+                    function_source(M, r"void mesh::set_coefficients\(\s*util::aligned::vector<coefficients_canonical> coefficients\)")]
     files = [("cl", "filter_structs.cpp"), ("cl", "filters.cpp"), ("cl", "utils.cpp"), ("program.cpp",), ("setup.cpp",),
              ("postprocessor", "node.cpp"), ("postprocessor", "directional_receiver.cpp"),
              ("preprocessor", "gaussian.cpp")]
@@ -346,7 +348,8 @@ def host_run_program() -> str:
         "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
         "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <stdexcept>", "#include <vector>",
     ] + ['#include "%s"' % os.path.join(wg, *f) for f in files] + [
-        '#include "waveguide/waveguide.h"', '#include "waveguide/preprocessor/hard_source.h"',
+        '#include "waveguide/waveguide.h"', '#include "waveguide/canonical.h"',
+        '#include "waveguide/preprocessor/hard_source.h"',
         '#include "waveguide/preprocessor/soft_source.h"', '#include "core/callback_accumulator.h"',
         "namespace wayverb { namespace waveguide {"] + mesh_members + ["} }",
         '#include "%s"' % os.path.join(HERE, "hostrun_driver.inc"),

@@ -122,6 +122,9 @@ def lib():
         L.refk_run_waveguide.restype = i
         L.refk_run_waveguide.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i, sz, vp, sz, vp, vp, sz, vp,
                                          sz, d, d, vp, vp, C.c_char_p, sz]
+        L.refk_canonical.restype = i
+        L.refk_canonical.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, d, d, sz, d, d, d,
+                                     vp, sz, vp, vp, vp, C.c_char_p, sz]
         L.refk_hm_to_impedance.argtypes = [vp, vp, vp, vp]
         L.refk_hm_to_flat.argtypes = [d, vp, vp]
         L.refk_hm_is_stable.restype = i
@@ -683,3 +686,39 @@ def run_waveguide(mesh, source_node=0, signal=(), receivers=(), soft=False, gaus
     if status:
         raise RuntimeError(err.value.decode())
     return done.value, out[:done.value], (dout[:done.value] if directional is not None else None)
+
+
+def canonical(mesh, surfaces, source, receiver, simulation_time, spacing, min_corner=(0.0, 0.0, 0.0), bands=0,
+              cutoff=500.0, usable_portion=0.6, speed_of_sound=340.0, acoustic_impedance=400.0, capacity_steps=4096):
+    """waveguide::canonical (canonical.h:97-177) as the reference wrote it: bands == 0 is the
+    single_band_parameters overload, otherwise the multiple-band one (flat coefficients per band from
+    `surfaces`, SURF_DT-like [n, 16] floats; the mesh must hold one coefficient set per surface).
+    -> None when the reference returned nullopt, else a list of bands
+       {"directional": float32 [steps, 4] (intensity xyz, pressure), "sample_rate", "valid_hz": (min, max)},
+       and the number of times the pressure callback ran. Raises RuntimeError with the reference's text."""
+    mc = np.asarray(min_corner, np.float32)
+    dims = np.asarray(mesh.dims, np.int32)
+    nodes = np.ascontiguousarray(mesh.nodes, NODE_DT)
+    coeffs = np.ascontiguousarray(mesh.coeffs, COEFF_DT)
+    b1 = np.ascontiguousarray(mesh.b1, np.uint32).reshape(-1, 1)
+    b2 = np.ascontiguousarray(mesh.b2, np.uint32).reshape(-1, 2)
+    b3 = np.ascontiguousarray(mesh.b3, np.uint32).reshape(-1, 3)
+    surf = np.ascontiguousarray(surfaces, np.float32).reshape(-1, 16)
+    src, rcv = np.asarray(source, np.float32), np.asarray(receiver, np.float32)
+    n_out = max(int(bands), 1)
+    out = np.zeros((n_out, capacity_steps, 4), np.float32)
+    band3 = np.zeros((n_out, 3), np.float64)
+    steps, calls = C.c_size_t(0), C.c_size_t(0)
+    err = C.create_string_buffer(512)
+    n = lib().refk_canonical(_p(mc), _p(dims), float(spacing), _p(nodes), nodes.size, _p(coeffs), coeffs.size,
+                             _p(b1), b1.shape[0], _p(b2), b2.shape[0], _p(b3), b3.shape[0], _p(surf), surf.shape[0],
+                             _p(src), _p(rcv), float(speed_of_sound), float(acoustic_impedance), int(bands),
+                             float(cutoff), float(usable_portion), float(simulation_time), _p(out), capacity_steps,
+                             _p(band3), C.byref(steps), C.byref(calls), err, 512)
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    if n == 0:
+        return None, calls.value
+    assert steps.value <= capacity_steps
+    return [{"directional": out[b, :steps.value].copy(), "sample_rate": band3[b, 0],
+             "valid_hz": (band3[b, 1], band3[b, 2])} for b in range(n)], calls.value

@@ -134,3 +134,61 @@ def test_directional_receiver_next_to_a_wall_is_refused():
     om = wgo.mesh_from_inside(wgo.cuboid_inside((8, 8, 8)), [wgo.to_flat(0.1)])
     with pytest.raises(RuntimeError, match="adjacent to a boundary"):
         refk.run_waveguide(om, 0, np.zeros(2), [om.index(4, 4, 4)], directional=(om.index(0, 4, 4), 1000.0, 1.2))
+
+
+def test_canonical_single_band_is_the_references():
+    """canonical.h:24-110 on the scenario of tests/test_cpp_shim.py::test_canonical_single_band_matches_oracle:
+    the node the source / receiver positions round to, the calibrated impulse, ceil(sample_rate * time)
+    steps, the sample rate, valid_hz -- from the reference's own header -- and the receiver pressure
+    against the oracle's loop."""
+    dims, spacing = (28, 26, 24), np.float32(0.05)
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [wgo.to_flat(0.2)])
+    source, receiver = (0.52, 0.61, 0.48), (0.86, 0.59, 0.51)
+    rate = refk.hm_rates(spacing, 340.0)[0]
+    surfaces = np.zeros((1, 16), np.float32)
+    bands, calls = refk.canonical(om, surfaces, source, receiver, 120.2 / rate, float(spacing))
+    assert len(bands) == 1 and calls == 121
+    band = bands[0]
+    assert band["directional"].shape == (121, 4) and band["sample_rate"] == rate and band["valid_hz"] == (0.0, 500.0)
+    # what the GPU test expects of the shim, now read off the reference itself
+    loc = lambda p: [int(np.round(np.float32(v) / spacing)) for v in p]  # noqa: E731
+    src, rcv = om.index(*loc(source)), om.index(*loc(receiver))
+    amp = np.float32(np.sqrt(400.0 / (4 * np.pi)) / (0.3405 * np.float64(spacing)))
+    assert amp == np.float32(refk.lib().refk_hm_calibration_factor(float(spacing), 400.0))
+    sig = np.zeros(121)
+    sig[0] = float(amp)
+    done, want, flag = wgo.Sim(om, "float").run(src, sig, [rcv])
+    assert done == 121 and flag == 0
+    assert np.array_equal(band["directional"][:, 3], want[:, 0].astype(np.float32))
+    assert np.abs(band["directional"][:, :3]).max() > 0
+    # a position outside the mesh (canonical.h:42-50)
+    with pytest.raises(RuntimeError, match="outside"):
+        refk.canonical(om, surfaces, (-5.0, 0.0, 0.0), receiver, 120.2 / rate, float(spacing))
+
+
+def test_canonical_multiple_bands_is_the_references():
+    """canonical.h:140-177: one run per band with that band's flat coefficients, band edges of
+    hrtf_band_params_hz -- the same expectations tests/cpp/test_waveguide_shim.cpp holds the shim to"""
+    dims, spacing = (20, 18, 16), np.float32(0.05)
+    absorption = [0.05, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7]
+    om = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [wgo.to_flat(0.9)])      # overwritten per band
+    surfaces = np.zeros((1, 16), np.float32)
+    surfaces[0, :8] = absorption
+    source, receiver = (0.42, 0.41, 0.38), (0.61, 0.49, 0.41)
+    rate = refk.hm_rates(spacing, 340.0)[0]
+    bands, calls = refk.canonical(om, surfaces, source, receiver, 60.5 / rate, float(spacing), bands=3)
+    assert len(bands) == 3 and calls == 3 * 61
+    loc = lambda p: [int(np.round(np.float32(v) / spacing)) for v in p]  # noqa: E731
+    src, rcv = om.index(*loc(source)), om.index(*loc(receiver))
+    amp = np.float32(np.sqrt(400.0 / (4 * np.pi)) / (0.3405 * np.float64(spacing)))
+    sig = np.zeros(61)
+    sig[0] = float(amp)
+    for b, band in enumerate(bands):
+        assert band["valid_hz"][0] == pytest.approx(20.0 * 1000.0 ** (b / 8.0), rel=1e-14)
+        assert band["valid_hz"][1] == pytest.approx(20.0 * 1000.0 ** ((b + 1) / 8.0), rel=1e-14)
+        flat = wgo.to_flat(float(np.float32(absorption[b])))                    # surface.absorption.s[band] is a float
+        mb = wgo.mesh_from_inside(wgo.cuboid_inside(dims), [flat])
+        done, want, flag = wgo.Sim(mb, "float").run(src, sig, [rcv])
+        assert done == 61 and flag == 0
+        assert np.array_equal(band["directional"][:, 3], want[:, 0].astype(np.float32))
+    assert not np.array_equal(bands[0]["directional"], bands[2]["directional"])
