@@ -327,31 +327,40 @@ def host_math_program() -> str:
     ]) + "\n"
 
 
+def single_file_unit(*rel) -> "callable":
+    """A translation unit that is one reference .cpp file, #included where it lies (files that each
+    define a file-local `source` string cannot share a unit)."""
+    def make() -> str:
+        return "\n".join([
+            "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+            "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
+            "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <stdexcept>", "#include <vector>",
+            '#include "%s"' % os.path.join(REF, "src", *rel),
+        ]) + "\n"
+    return make
+
+
 def host_run_program() -> str:
-    """The reference's waveguide HOST loop -- the waveguide::run template, program.cpp's class, setup.cpp,
-    the stock processors -- whole files #included where they lie over the host-memory cl.hpp stand-in
-    (hostcl/). From mesh.cpp only the constructor and the two getters are taken (the rest of that file
-    builds meshes with further OpenCL programs)."""
+    """The reference's waveguide HOST code -- the waveguide::run template and canonical.h, the program
+    classes, setup.cpp, the stock processors, and mesh construction (mesh.cpp, boundary_adjust.cpp,
+    boundary_coefficient_finder.cpp with their programs) -- whole files #included where they lie over
+    the host-memory cl.hpp stand-in (hostcl/)."""
     src = os.path.join(REF, "src")
     wg = os.path.join(src, "waveguide", "src")
-    M = "src/waveguide/src/mesh.cpp"
-    mesh_members = [function_source(M, r"mesh::mesh\(mesh_descriptor descriptor, vectors vectors\)"),
-                    function_source(M, r"const mesh_descriptor& mesh::get_descriptor\(\) const "),
-                    function_source(M, r"const vectors& mesh::get_structure\(\) const "),
-                    function_source(M, r"void mesh::set_coefficients\(coefficients_canonical coefficients\)"),
-                    function_source(M, r"void mesh::set_coefficients\(\s*util::aligned::vector<coefficients_canonical> coefficients\)")]
     files = [("cl", "filter_structs.cpp"), ("cl", "filters.cpp"), ("cl", "utils.cpp"), ("program.cpp",), ("setup.cpp",),
              ("postprocessor", "node.cpp"), ("postprocessor", "directional_receiver.cpp"),
-             ("preprocessor", "gaussian.cpp")]
+             ("preprocessor", "gaussian.cpp"), ("boundary_coefficient_finder.cpp",), ("boundary_adjust.cpp",),
+             ("mesh.cpp",)]
+    core_cl = [os.path.join(src, "core", "src", "cl", f) for f in ("geometry.cpp", "voxel.cpp")]
     return "\n".join([
         "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
         "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
         "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <stdexcept>", "#include <vector>",
-    ] + ['#include "%s"' % os.path.join(wg, *f) for f in files] + [
+    ] + ['#include "%s"' % f for f in core_cl] + ['#include "%s"' % os.path.join(wg, *f) for f in files] + [
         '#include "waveguide/waveguide.h"', '#include "waveguide/canonical.h"',
         '#include "waveguide/preprocessor/hard_source.h"',
         '#include "waveguide/preprocessor/soft_source.h"', '#include "core/callback_accumulator.h"',
-        "namespace wayverb { namespace waveguide {"] + mesh_members + ["} }",
+    ] + [
         '#include "%s"' % os.path.join(HERE, "hostrun_driver.inc"),
     ]) + "\n"
 
@@ -389,8 +398,10 @@ def host_pp_program() -> str:
     ]) + "\n"
 
 
-HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program, "ref_hostrun.cpp": host_run_program}
-HOSTCL_UNITS = {"ref_hostrun.cpp"}     # compiled with hostcl/ (the cl.hpp stand-in) in front
+HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program, "ref_hostrun.cpp": host_run_program,
+              "ref_hostrun_setup_program.cpp": single_file_unit("waveguide", "src", "mesh_setup_program.cpp"),
+              "ref_hostrun_bcoef_program.cpp": single_file_unit("waveguide", "src", "boundary_coefficient_program.cpp")}
+HOSTCL_UNITS = {"ref_hostrun.cpp", "ref_hostrun_setup_program.cpp", "ref_hostrun_bcoef_program.cpp"}     # compiled with hostcl/ (the cl.hpp stand-in) in front
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
                  "-I", os.path.join(REF, "src", "utilities", "include"),
                  "-I", os.path.join(REF, "src", "raytracer", "include"),

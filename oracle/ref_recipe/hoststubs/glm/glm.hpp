@@ -22,6 +22,7 @@
 
 #include <cmath>
 #include <cstddef>
+#include <limits>   // GLM pulls it in; core/almost_equal.h relies on that
 
 namespace glm {
 

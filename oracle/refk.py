@@ -122,6 +122,10 @@ def lib():
         L.refk_run_waveguide.restype = i
         L.refk_run_waveguide.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i, sz, vp, sz, vp, vp, sz, vp,
                                          sz, d, d, vp, vp, C.c_char_p, sz]
+        L.refk_compute_mesh.restype = i
+        L.refk_compute_mesh.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, d, f, f, YULEWALK_CB, vp, vp, vp, vp,
+                                        C.c_char_p, sz]
+        L.refk_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
         L.refk_canonical.restype = i
         L.refk_canonical.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, d, d, sz, d, d, d,
                                      vp, sz, vp, vp, vp, C.c_char_p, sz]
@@ -722,3 +726,42 @@ def canonical(mesh, surfaces, source, receiver, simulation_time, spacing, min_co
     assert steps.value <= capacity_steps
     return [{"directional": out[b, :steps.value].copy(), "sample_rate": band3[b, 0],
              "valid_hz": (band3[b, 1], band3[b, 2])} for b in range(n)], calls.value
+
+
+class RefMesh:
+    """what waveguide::mesh holds (mesh.h:13-31): descriptor + vectors"""
+
+    def __init__(self, min_corner, dims, spacing, nodes, coeffs, b1, b2, b3, voxel_aabb):
+        self.min_corner, self.dims, self.spacing = min_corner, tuple(int(v) for v in dims), spacing
+        self.nodes, self.coeffs, self.b1, self.b2, self.b3 = nodes, coeffs, b1, b2, b3
+        self.voxel_aabb = voxel_aabb
+
+
+def compute_mesh(sc, fit, mesh_spacing=None, speed_of_sound=340.0, depth=5, padding=0.1, anchor=None, sample_rate=None):
+    """The reference's own mesh construction, run on the host (mesh.cpp, boundary_coefficient_finder.cpp,
+    boundary_adjust.cpp with their programs' kernels as compiled for the host):
+      anchor=None : compute_mesh(cc, make_voxelised_scene_data(scene, depth, padding), mesh_spacing, c)
+      anchor=xyz  : compute_voxels_and_mesh(cc, scene, anchor, sample_rate, c) -- what the engine calls
+    `fit(order, f, m) -> (b, a)` is the Yule-Walker fit the IT++ stand-in forwards to. -> RefMesh"""
+    v, t, s = _scene_arrays(sc)
+
+    def cb(order, n, f, m, b_out, a_out):
+        b, a = fit(order, np.array(f[:n]), np.array(m[:n]))
+        for k in range(order + 1):
+            b_out[k], a_out[k] = float(b[k]), float(a[k])
+    mc, dims, sp = np.zeros(3, np.float32), np.zeros(3, np.int32), np.zeros(1, np.float32)
+    counts = np.zeros(5, np.uint64)
+    err = C.create_string_buffer(512)
+    an = None if anchor is None else np.asarray(anchor, np.float32)
+    status = lib().refk_compute_mesh(_p(v), v.shape[0], _p(t), t.shape[0], _p(s), s.shape[0], int(depth), float(padding),
+                                     None if an is None else _p(an), float(sample_rate or 0.0),
+                                     float(mesh_spacing or 0.0), float(speed_of_sound), YULEWALK_CB(cb), _p(mc), _p(dims),
+                                     _p(sp), _p(counts), err, 512)
+    if status:
+        raise RuntimeError(err.value.decode())
+    n, nc, n1, n2, n3 = (int(c) for c in counts)
+    nodes, coeffs = np.zeros(n, NODE_DT), np.zeros(nc, COEFF_DT)
+    b1, b2, b3 = np.zeros((n1, 1), np.uint32), np.zeros((n2, 2), np.uint32), np.zeros((n3, 3), np.uint32)
+    aabb = np.zeros(6, np.float32)
+    lib().refk_mesh_read(_p(nodes), _p(coeffs), _p(b1), _p(b2), _p(b3), _p(aabb))
+    return RefMesh(mc, dims, float(sp[0]), nodes, coeffs, b1, b2, b3, aabb)

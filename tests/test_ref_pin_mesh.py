@@ -1,7 +1,9 @@
 """Pins the oracle's mesh-construction restatement to the REFERENCE'S OWN kernel source:
 set_node_inside / set_node_boundary_type (src/waveguide/src/mesh_setup_program.cpp:110-172) and
 boundary_coefficient_finder_1d/2d/3d (boundary_coefficient_program.cpp:310-484), compiled from
-/root/reference into oracle/_ref by oracle/ref_recipe/build.py. Node for node, index for index."""
+/root/reference into oracle/_ref by oracle/ref_recipe/build.py. Node for node, index for index.
+The second half runs the reference's own HOST side as well (compute_mesh / compute_voxels_and_mesh of
+mesh.cpp, boundary_coefficient_finder.cpp, boundary_adjust.cpp over a host-memory cl.hpp stand-in)."""
 import numpy as np
 import pytest
 
@@ -93,3 +95,78 @@ def test_inside_test_on_an_l_shaped_solid():
     ref_nodes = refk.classify_scene(sc, mc, dims, sp)
     assert np.array_equal(ref_nodes["boundary_type"] == wgo.ID_INSIDE, ins.ravel())
     assert ins.any() and not ins[7, 7, 7]   # the doubly-enclosed core counts as outside
+
+
+# ---- the reference's own HOST side of mesh construction, run on the host --------------------------------
+# mesh.cpp (compute_mesh, compute_voxels_and_mesh), boundary_coefficient_finder.cpp, boundary_adjust.cpp,
+# setup.cpp and the program classes, compiled unmodified over the host-memory cl.hpp stand-in and
+# enqueueing the kernels above (refk.compute_mesh): no restated numbering, no Python-driven sequence.
+def oracle_mesh(sc, ref):
+    """what tests/test_mesh_build.py compares the device mesh builder with, on the reference's descriptor"""
+    o = rto.Scene(sc)
+    sp = np.float32(ref.spacing)
+    ins = o.nodes_inside(ref.min_corner, ref.dims, sp)
+    z, y, x = np.indices(ins.shape)
+    pts = np.stack([ref.min_corner[0] + x.astype(np.float32) * sp, ref.min_corner[1] + y.astype(np.float32) * sp,
+                    ref.min_corner[2] + z.astype(np.float32) * sp], -1).reshape(-1, 3)
+    surf, _ = o.closest_surface(pts)
+    return wgo.mesh_from_inside(ins, [wgo.to_flat(0.1)] * len(sc.surfaces), surf)
+
+
+def fit(order, f, m):
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import lrs as olrs
+    return olrs.yulewalk(order, list(f), list(m))
+
+
+def assert_same_mesh(ref, om):
+    assert np.array_equal(ref.nodes["boundary_type"], om.nodes["boundary_type"])
+    assert np.array_equal(ref.nodes["boundary_index"], om.nodes["boundary_index"])
+    assert np.array_equal(ref.b1, om.b1) and np.array_equal(ref.b2, om.b2) and np.array_equal(ref.b3, om.b3)
+
+
+def test_compute_mesh_of_the_reference_on_a_box_with_three_materials():
+    b = room()
+    sc = scene.Scene(b.vertices, b.triangles, b.surfaces, voxeliser="octree", depth=5)
+    ref = refk.compute_mesh(sc, fit, mesh_spacing=0.25, depth=5, padding=0.1)
+    # the descriptor compute_mesh derives from the voxelised scene's box (mesh.cpp:64-71)
+    assert np.array_equal(ref.min_corner, sc.aabb[:3]) and ref.spacing == 0.25
+    assert ref.dims == tuple(int(v) for v in ((sc.aabb[3:] - sc.aabb[:3]) / np.float32(0.25)).astype(np.int32))
+    om = oracle_mesh(sc, ref)
+    assert_same_mesh(ref, om)
+    assert ref.b1.shape[0] > 500 and ref.b2.shape[0] > 30 and len(set(ref.b1.ravel().tolist())) == 3
+    # one coefficient set per surface: to_impedance(compute_reflectance_filter_coefficients(absorption,
+    # 1 / time_step)) (mesh.cpp:126-137) -- with the same fit, the oracle's numbers exactly
+    import lrs as olrs
+    rate = refk.hm_rates(0.25, 340.0)[0]
+    assert ref.coeffs.size == 3
+    for k in range(3):
+        rb, ra = olrs.reflectance_filter(sc.surfaces["absorption"][k].astype(np.float64), rate)
+        ib, ia = olrs.to_impedance(rb, ra)
+        assert np.array_equal(ref.coeffs[k]["b"], ib) and np.array_equal(ref.coeffs[k]["a"], ia)
+
+
+def test_compute_voxels_and_mesh_of_the_reference_on_the_concert_hall():
+    """what the engine calls (mesh.cpp:143-160): boundary adjusted around the receiver, spacing from the
+    sample rate, 520 828 nodes. The reference voxelises on that adjusted box; the oracle (and the
+    product) walk the padded depth-5 grid -- the classification must not depend on it."""
+    sc, meta = scene.concert_hall(0)
+    tri = sc.triangles.copy()
+    tri["surface"] = np.arange(tri.size) % 3                  # three materials spread over the hall
+    surfaces = [scene.make_surface(0.1, 0.1), scene.make_surface(0.2, 0.1), scene.make_surface(0.3, 0.1)]
+    sc = scene.Scene(sc.vertices, tri, surfaces, voxeliser="octree", depth=5)
+    ref = refk.compute_mesh(sc, fit, anchor=meta["receiver"], sample_rate=1500.0)
+    # config::grid_spacing(c, 1 / sample_rate) (config.cpp:23-25) as a float, and boundary_adjust.cpp:8-22:
+    # the receiver sits on a node, two spare layers either side
+    assert ref.spacing == float(np.float32(340.0 * (1 / 1500.0) * np.sqrt(3.0)))
+    rel = (np.asarray(meta["receiver"], np.float32) - ref.min_corner) / np.float32(ref.spacing)
+    assert np.abs(rel - np.round(rel)).max() < 1e-3
+    assert (ref.min_corner < sc.aabb[:3] + 0.1 - ref.spacing).all()
+    assert np.array_equal(ref.voxel_aabb[:3], ref.min_corner)
+    om = oracle_mesh(sc, ref)
+    assert ref.nodes.size == om.nodes.size > 500000
+    assert_same_mesh(ref, om)
+    assert ref.b1.shape[0] > 20000 and ref.b2.shape[0] > 4000 and ref.b3.shape[0] > 100
+    assert len(set(ref.b1.ravel().tolist())) == 3
