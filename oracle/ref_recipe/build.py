@@ -304,14 +304,9 @@ def host_scene_program() -> str:
 def host_math_program() -> str:
     """The reference's small closed-form HOST functions that the product's host side restates: whole
     files where they compile (mesh_descriptor.cpp, config.cpp, frequency_domain_envelope.cpp, filters.cpp,
-    fitted_boundary.h & co. over an IT++ stand-in that forwards the fit), two functions of the OpenCL-bound
-    stochastic/finder.{h,cpp} taken singly."""
+    fitted_boundary.h & co. over an IT++ stand-in that forwards the fit)."""
     src = os.path.join(REF, "src")
     wg = os.path.join(src, "waveguide", "src")
-    energy_h = function_source("src/raytracer/include/raytracer/stochastic/finder.h",
-                               r"constexpr auto compute_ray_energy\(size_t total_rays,\s*float dist,\s*float open_angle\)\s*\{")
-    energy_cpp = function_source("src/raytracer/src/stochastic/finder.cpp",
-                                 r"float compute_ray_energy\(size_t total_rays,\s*const glm::vec3& source,")
     return "\n".join([
         "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
         "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
@@ -322,7 +317,9 @@ def host_math_program() -> str:
         '#include "%s"' % os.path.join(wg, "filters.cpp"),
         '#include "waveguide/fitted_boundary.h"', '#include "waveguide/calibration.h"',
         '#include "raytracer/optimum_reflection_number.h"', '#include "core/cl/scene_structs.h"',
-        "namespace wayverb { namespace raytracer { namespace stochastic {", energy_h, energy_cpp, "} } }",
+        # compute_ray_energy: stochastic/finder.cpp is compiled whole in ref_hostray.cpp (it needs the cl.hpp stand-in)
+        "namespace wayverb { namespace raytracer { namespace stochastic {",
+        "float compute_ray_energy(size_t, const glm::vec3&, const glm::vec3&, float);", "} } }",
         '#include "%s"' % os.path.join(HERE, "hostmath_driver.inc"),
     ]) + "\n"
 
@@ -365,6 +362,33 @@ def host_run_program() -> str:
     ]) + "\n"
 
 
+def host_ray_program() -> str:
+    """The reference's ray HOST code -- the raytracer::run template, reflector.cpp, stochastic/finder.cpp,
+    the reflection processors, canonical.cpp -- whole files #included where they lie over the host-memory
+    cl.hpp stand-in. While reflector.cpp is read std::random_device is spelled as a device that counts
+    up from a chosen seed (hostray_driver.inc says why); nothing else changes."""
+    src = os.path.join(REF, "src")
+    rt = os.path.join(src, "raytracer", "src")
+    files = [("stochastic", "finder.cpp"), ("reflection_processor", "image_source.cpp"),
+             ("reflection_processor", "stochastic_histogram.cpp"), ("reflection_processor", "visual.cpp"),
+             ("canonical.cpp",)]
+    return "\n".join([
+        "// GENERATED by oracle/ref_recipe/build.py from /root/reference -- do not commit.",
+        "#include <algorithm>", "#include <array>", "#include <cmath>", "#include <cstring>", "#include <functional>",
+        "#include <future>", "#include <iostream>", "#include <memory>", "#include <numeric>", "#include <random>",
+        "#include <stdexcept>", "#include <vector>",
+        "static unsigned refk_ray_seed_value = 1;",
+        "namespace std { struct refk_counting_device { unsigned operator()() const { return refk_ray_seed_value++; } }; }",
+        "#define random_device refk_counting_device",
+        '#include "%s"' % os.path.join(rt, "reflector.cpp"),
+        "#undef random_device",
+        '#include "%s"' % os.path.join(src, "core", "src", "azimuth_elevation.cpp"),
+    ] + ['#include "%s"' % os.path.join(rt, *f) for f in files] + [
+        '#include "raytracer/raytracer.h"',
+        '#include "%s"' % os.path.join(HERE, "hostray_driver.inc"),
+    ]) + "\n"
+
+
 def host_pp_program() -> str:
     """The reference's HOST post-processing code: raytracer/src/stochastic/postprocessing.cpp and the
     whole frequency_domain library as files (#included where they lie) over the FFTW stand-in of
@@ -400,8 +424,13 @@ def host_pp_program() -> str:
 
 HOST_UNITS = {"ref_scene.cpp": host_scene_program, "ref_pp.cpp": host_pp_program, "ref_hostmath.cpp": host_math_program, "ref_hostrun.cpp": host_run_program,
               "ref_hostrun_setup_program.cpp": single_file_unit("waveguide", "src", "mesh_setup_program.cpp"),
-              "ref_hostrun_bcoef_program.cpp": single_file_unit("waveguide", "src", "boundary_coefficient_program.cpp")}
-HOSTCL_UNITS = {"ref_hostrun.cpp", "ref_hostrun_setup_program.cpp", "ref_hostrun_bcoef_program.cpp"}     # compiled with hostcl/ (the cl.hpp stand-in) in front
+              "ref_hostrun_bcoef_program.cpp": single_file_unit("waveguide", "src", "boundary_coefficient_program.cpp"),
+              "ref_hostray.cpp": host_ray_program,
+              "ref_hostray_program.cpp": single_file_unit("raytracer", "src", "program.cpp"),
+              "ref_hostray_stoch_program.cpp": single_file_unit("raytracer", "src", "stochastic", "program.cpp"),
+              "ref_hostray_brdf.cpp": single_file_unit("raytracer", "src", "cl", "brdf.cpp")}
+HOSTCL_UNITS = {"ref_hostrun.cpp", "ref_hostrun_setup_program.cpp", "ref_hostrun_bcoef_program.cpp", "ref_hostray.cpp",
+                "ref_hostray_program.cpp", "ref_hostray_stoch_program.cpp", "ref_hostray_brdf.cpp"}     # compiled with hostcl/ (the cl.hpp stand-in) in front
 HOST_INCLUDES = ["-I", os.path.join(HERE, "hoststubs"), "-I", os.path.join(REF, "src", "core", "include"),
                  "-I", os.path.join(REF, "src", "utilities", "include"),
                  "-I", os.path.join(REF, "src", "raytracer", "include"),

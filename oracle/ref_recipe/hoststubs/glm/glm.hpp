@@ -71,6 +71,9 @@ using vec3 = tvec3<float>;
 using uvec3 = tvec3<unsigned>;
 using ivec3 = tvec3<int>;
 using dvec3 = tvec3<double>;
+struct mat4 final {   // named in core/orientation.h's declarations only; nothing compiled here touches a matrix
+    float m[16];
+};
 using bvec3 = tvec3<bool>;
 using bvec2 = tvec2<bool>;
 

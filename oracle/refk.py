@@ -122,6 +122,11 @@ def lib():
         L.refk_run_waveguide.restype = i
         L.refk_run_waveguide.argtypes = [vp, vp, f, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i, sz, vp, sz, vp, vp, sz, vp,
                                          sz, d, d, vp, vp, C.c_char_p, sz]
+        L.refk_ray_direction_rng.argtypes = [u, sz, vp]
+        L.refk_ray_run.restype = i
+        L.refk_ray_run.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, vp, d, d, vp, sz, u, sz, sz, sz, f, f, i, sz, vp, vp,
+                                   C.c_char_p, sz]
+        L.refk_ray_read.argtypes = [vp, vp, vp]
         L.refk_compute_mesh.restype = i
         L.refk_compute_mesh.argtypes = [vp, sz, vp, sz, vp, sz, sz, f, vp, d, f, f, YULEWALK_CB, vp, vp, vp, vp,
                                         C.c_char_p, sz]
@@ -765,3 +770,45 @@ def compute_mesh(sc, fit, mesh_spacing=None, speed_of_sound=340.0, depth=5, padd
     aabb = np.zeros(6, np.float32)
     lib().refk_mesh_read(_p(nodes), _p(coeffs), _p(b1), _p(b2), _p(b3), _p(aabb))
     return RefMesh(mc, dims, float(sp[0]), nodes, coeffs, b1, b2, b3, aabb)
+
+
+# ---- the reference's own raytracer::run template, compiled for the host -------------------------------
+def ray_direction_rng(seed, n):
+    """get_direction_rng (reflector.cpp:13-25) with its engine seeded by `seed` -> float32 [n, 2] (z, theta)"""
+    out = np.zeros((n, 2), np.float32)
+    lib().refk_ray_direction_rng(int(seed), int(n), _p(out))
+    return out
+
+
+def ray_run(sc, source, receiver, directions, seed, image_source_order, specular_from_step=None, total_rays=None,
+            receiver_radius=0.1, histogram_rate=1000.0, directional=False, visual_items=0, speed_of_sound=340.0,
+            acoustic_impedance=400.0, depth=5, padding=0.1):
+    """raytracer::run (raytracer.h:188-266) as the reference wrote it -- reflector.cpp, stochastic/finder.cpp,
+    the image-source / histogram / visual processors -- over the host-memory cl.hpp stand-in, enqueueing
+    the reference's kernels as compiled for the host. The engine behind each step's (z, theta) draws is
+    seeded seed, seed + 1, ... (one per reflector::run_step, in order): ray_direction_rng(seed + k, n)
+    reproduces the k-th.
+    -> dict(impulses, histogram float32 [bins, 8] or [20, 9, bins, 8], visual REFL_DT [steps, items],
+            depth, segments_reported)"""
+    v, t, s = _scene_arrays(sc)
+    src, rcv = np.asarray(source, np.float32), np.asarray(receiver, np.float32)
+    dirs = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+    counts = np.zeros(4, np.uint64)
+    dep = C.c_size_t(0)
+    err = C.create_string_buffer(512)
+    order = int(image_source_order)
+    status = lib().refk_ray_run(_p(v), v.shape[0], _p(t), t.shape[0], _p(s), s.shape[0], int(depth), float(padding),
+                                _p(src), _p(rcv), float(speed_of_sound), float(acoustic_impedance), _p(dirs),
+                                dirs.shape[0], int(seed), order,
+                                int(dirs.shape[0] if total_rays is None else total_rays),
+                                int(order + 1 if specular_from_step is None else specular_from_step),
+                                float(receiver_radius), float(histogram_rate), int(directional), int(visual_items),
+                                _p(counts), C.byref(dep), err, 512)
+    if status:
+        raise RuntimeError(err.value.decode())
+    n_imp, bins, vsteps, calls = (int(c) for c in counts)
+    imp = np.zeros(n_imp, IMPULSE_DT)
+    hist = np.zeros((20, 9, bins, 8) if directional else (bins, 8), np.float32)
+    vis = np.zeros((vsteps, visual_items), REFL_DT)
+    lib().refk_ray_read(_p(imp) if n_imp else None, _p(hist) if hist.size else None, _p(vis) if vis.size else None)
+    return {"impulses": imp, "histogram": hist, "visual": vis, "depth": dep.value, "segments_reported": calls}
