@@ -39,7 +39,11 @@
 // `stochastic` kernels with their geometry / voxel / brdf sources are compiled for the host into
 // oracle/_ref by oracle/ref_recipe/build.py; tests/test_ref_pin_rt.py feeds both sides the same
 // directions and random stream and asserts the reflection records of every step bit-identical
-// and the histograms equal to 1e-12. On top: the reference's CPU-twin tests restated in
+// and the histograms equal to 1e-12. The HOST side runs too: the reference's own raytracer::run
+// template with reflector.cpp, finder.cpp and the reflection processors
+// (tests/test_ref_pin_ray_run.py), its histogram binning and look-up-table indexing
+// (incremental_histogram, vector_look_up_table::index), compute_ray_energy and
+// compute_optimum_reflection_number (tests/test_ref_pin_hostmath.py). On top: the reference's CPU-twin tests restated in
 // tests/test_rt_oracle_kats.py (brute-force == voxel traversal, analytic shoebox image sources,
 // energy equivalence).
 

@@ -31,6 +31,10 @@
 // compiled for the host by oracle/ref_recipe/build.py; tests/test_ref_pin_wg.py steps it and this
 // file on the same meshes and asserts bit identity of pressures, filter memories and error flags
 // in both arithmetic modes, tests/test_ref_pin_mesh.py does the same for the mesh-setup kernels.
+// The HOST side runs too: the reference's own waveguide::run template with its stock processors and
+// canonical.h (tests/test_ref_pin_run.py holds wgo_run below against it bit for bit), its mesh
+// construction (compute_mesh & co., tests/test_ref_pin_mesh.py) and its coefficient helpers
+// (tests/test_ref_pin_hostmath.py), compiled unmodified over the stand-ins of oracle/ref_recipe/.
 // On top: the reference's own known-answer tests (tests/test_oracle_kats.py) and the nine
 // checked-in coefficient sets of bin/boundary_test/output.soft/coefficients.txt (tests/golden/).
 //
