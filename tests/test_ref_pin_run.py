@@ -192,3 +192,49 @@ def test_canonical_multiple_bands_is_the_references():
         assert done == 61 and flag == 0
         assert np.array_equal(band["directional"][:, 3], want[:, 0].astype(np.float32))
     assert not np.array_equal(bands[0]["directional"], bands[2]["directional"])
+
+
+@pytest.mark.parametrize("cutoff", [500.0, 1000.0])
+def test_baseline_config_1_end_to_end_against_the_reference_itself(cutoff):
+    """BASELINE.json configs[0]: 5 x 4 x 3 m shoebox, absorption 0.1, source
+    (1, 1, 1), receiver (2, 3, 1.5), single_band_parameters{cutoff, 0.6} -- the reference's own CPU-
+    runnable case, run here by the reference's own code from the scene onwards: adjusted boundary around
+    the receiver, depth-5 voxelisation, compute_mesh with its fitted wall filters, canonical(). The
+    oracle's pipeline on the same descriptor (voxel inside test, classification, closest surface, the
+    float-mode stepping loop) must return the same receiver pressures, bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lrs as olrs
+    from oracle import rto
+    from wayverb_b200 import scene
+
+    def fit(order, f, m):
+        return olrs.yulewalk(order, list(f), list(m))
+
+    b = scene.box_scene((5.0, 4.0, 3.0), subdiv=1, surfaces=[scene.make_surface(0.1, 0.1)])
+    sc = scene.Scene(b.vertices, b.triangles, b.surfaces, voxeliser="octree", depth=5)
+    src, rcv = (1.0, 1.0, 1.0), (2.0, 3.0, 1.5)
+    fs = cutoff / (0.25 * 0.6)                                # compute_sampling_frequency, simulation_parameters.h:65-68
+    ref = refk.compute_mesh(sc, fit, anchor=rcv, sample_rate=fs)
+    assert ref.dims == {500.0: (33, 26, 22), 1000.0: (60, 50, 37)}[cutoff]
+    bands, calls = refk.canonical(ref, np.zeros((1, 16), np.float32), src, rcv, 0.1, spacing=ref.spacing,
+                                  min_corner=ref.min_corner, cutoff=cutoff, capacity_steps=8192)
+    steps = int(np.ceil(bands[0]["sample_rate"] * 0.1))
+    assert len(bands) == 1 and calls == steps == bands[0]["directional"].shape[0]
+    assert bands[0]["valid_hz"] == (0.0, cutoff) and abs(bands[0]["sample_rate"] - fs) < 1e-3
+
+    o = rto.Scene(sc)
+    sp = np.float32(ref.spacing)
+    ins = o.nodes_inside(ref.min_corner, ref.dims, sp)
+    z, y, x = np.indices(ins.shape)
+    pts = np.stack([ref.min_corner[0] + x.astype(np.float32) * sp, ref.min_corner[1] + y.astype(np.float32) * sp,
+                    ref.min_corner[2] + z.astype(np.float32) * sp], -1).reshape(-1, 3)
+    surf, _ = o.closest_surface(pts)
+    om = wgo.mesh_from_inside(ins, [ref.coeffs[0]], surf)
+    assert np.array_equal(om.nodes["boundary_type"], ref.nodes["boundary_type"])
+    loc = lambda p: [int(np.round((np.float32(v) - m) / sp)) for v, m in zip(p, ref.min_corner)]  # noqa: E731
+    sig = np.zeros(steps)
+    sig[0] = float(np.float32(refk.lib().refk_hm_calibration_factor(float(sp), 400.0)))
+    done, want, flag = wgo.Sim(om, "float").run(om.index(*loc(src)), sig, [om.index(*loc(rcv))])
+    assert done == steps and flag == 0 and np.abs(want).max() > 0.1
+    assert np.array_equal(bands[0]["directional"][:, 3], want[:, 0].astype(np.float32))
