@@ -2,9 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY. Nothing in wayverb_b200/ may import or load what this produces.
 
-The reference's device code is OpenCL-C held in C++ raw-string literals. Its host side
-(glm, OpenCL-CLHPP, IT++ ... fetched at configure time) cannot be built in this image, but the
-kernel strings can: this recipe
+The reference's device code is OpenCL-C held in C++ raw-string literals. Its own build cannot run in
+this image (glm, OpenCL-CLHPP, FFTW, IT++, libsamplerate ... are fetched at configure time), but the
+kernel strings compile for the host, and so do its host sources behind stand-ins for those
+dependencies (HOST_UNITS below, hoststubs/, hostcl/). For the kernels this recipe
 
   1. reads the raw-string literals out of the files under /root/reference where they lie
      (never copied into the repository: every output goes to oracle/_ref/, which is
@@ -20,7 +21,11 @@ kernel strings can: this recipe
 Build flags: -O2 -ffp-contract=off (no FMA contraction), so what executes is the operation order
 of the reference source.
 
-Usage: python oracle/ref_recipe/build.py [--force]
+The host units are plain translation units that #include the reference's .cpp files by path (whole
+files; single functions only where the rest of a file needs something that is not stood in for), then a
+driver (*_driver.inc) with the extern "C" entry points oracle/refk.py binds.
+
+Usage: python oracle/ref_recipe/build.py [--force]        (WVB_REFERENCE_ROOT=<checkout> for another tree)
 """
 from __future__ import annotations
 
