@@ -20,9 +20,14 @@
 // These are the only places where this file, and not the reference's source, decides arithmetic.
 #pragma once
 
+#include <cassert>
+#include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstddef>
-#include <limits>   // GLM pulls it in; core/almost_equal.h relies on that
+#include <cstdlib>
+#include <limits>   // GLM pulls these in; core/almost_equal.h (numeric_limits) relies on that
+#include <type_traits>
 
 namespace glm {
 
@@ -108,6 +113,9 @@ GLM_STUB_BINOP2(+)
 GLM_STUB_BINOP2(-)
 GLM_STUB_BINOP2(*)
 GLM_STUB_BINOP2(/)
+GLM_STUB_BINOP2(%)
+GLM_STUB_BINOP2(&)
+GLM_STUB_BINOP2(<<)
 #undef GLM_STUB_BINOP2
 template <typename T> constexpr bool operator==(const tvec2<T>& a, const tvec2<T>& b) { return a.x == b.x && a.y == b.y; }
 template <typename T> constexpr bool operator!=(const tvec2<T>& a, const tvec2<T>& b) { return !(a == b); }
@@ -132,6 +140,11 @@ inline float inversesqrt(float x) { return 1.0f / std::sqrt(x); }
 inline vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }
 inline float length(const vec3& v) { return std::sqrt(dot(v, v)); }
 inline float distance(const vec3& a, const vec3& b) { return length(b - a); }
+// the scalar forms (func_geometric.inl: length(x) = abs(x), distance(p0, p1) = length(p1 - p0))
+inline float length(float x) { return std::fabs(x); }
+inline double length(double x) { return std::fabs(x); }
+inline float distance(float a, float b) { return length(b - a); }
+inline double distance(double a, double b) { return length(b - a); }
 inline vec3 mix(const vec3& a, const vec3& b, float t) { return a + t * (b - a); }
 inline vec3 round(const vec3& v) { return vec3(std::round(v.x), std::round(v.y), std::round(v.z)); }
 inline vec3 ceil(const vec3& v) { return vec3(std::ceil(v.x), std::ceil(v.y), std::ceil(v.z)); }
