@@ -19,10 +19,13 @@ Left out, and why:
   * tests of code that is not on the path (dc blocker, schroeder, attenuators, orientation, ...).
 Known result: core/tests/vector_look_up_table.cpp's `index` and `pointing` cases expect +z to be "front";
 az_el.cpp has -z (compute_azimuth = atan2(x, -z), compute_pointing -> (0, 0, -1) for azimuth 0), so the
-reference fails these two itself. Two cases are statistical, seeded from std::random_device:
+reference fails these two itself. Three cases are statistical, seeded from std::random_device:
 multiband.noise (eight 20 % bounds on 40-bin estimates: passes about four times in five) and
 tri_cube_tests.comparison (two float implementations of the same predicate on 2^20 random triangles:
-about one disagreement per three million triangles, so it passes about two times in three).
+about one disagreement per three million triangles, so it passes about two times in three), and
+image_source.fast_pressure draws source and receiver anywhere in the room and needs 10 000 random rays to
+find every exact image source within 10 m, matched inside a window of neighbours by distance: it throws
+"No approximate matches." about one time in ten.
 
 Usage: python oracle/ref_recipe/build_tests.py [--all]  -> oracle/_ref/reftest_{core,raytracer,waveguide,frequency_domain}
        (--all: also the six-minute nan_in_waveguide run)
@@ -61,7 +64,7 @@ SLOW_GROUPS = {
 }
 # cases the reference's own code does not satisfy (see the docstring)
 KNOWN_STALE = {"vector_look_up_table.index", "vector_look_up_table.pointing"}
-STATISTICAL = {"multiband.noise", "tri_cube_tests.comparison"}
+STATISTICAL = {"multiband.noise", "tri_cube_tests.comparison", "image_source.fast_pressure"}
 
 
 def exe(group: str) -> str:
