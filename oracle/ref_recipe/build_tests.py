@@ -20,9 +20,9 @@ Left out, and why:
 Known result: core/tests/vector_look_up_table.cpp's `index` and `pointing` cases expect +z to be "front";
 az_el.cpp has -z (compute_azimuth = atan2(x, -z), compute_pointing -> (0, 0, -1) for azimuth 0), so the
 reference fails these two itself. Three cases are statistical, seeded from std::random_device:
-multiband.noise (eight 20 % bounds on 40-bin estimates: passes about four times in five) and
+multiband.noise (eight 20 % bounds on 40-bin estimates: passes about three times in five) and
 tri_cube_tests.comparison (two float implementations of the same predicate on 2^20 random triangles:
-about one disagreement per three million triangles, so it passes about two times in three), and
+about one disagreement per two million triangles, so it passes about three times in five), and
 image_source.fast_pressure draws source and receiver anywhere in the room and needs 10 000 random rays to
 find every exact image source within 10 m, matched inside a window of neighbours by distance: it throws
 "No approximate matches." about one time in ten.
