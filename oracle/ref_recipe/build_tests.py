@@ -9,9 +9,10 @@ host-memory command queue, a kernel launcher or the FFT were wrong, the referenc
 its geometry, ray kernels, image sources, histograms, waveguide and filter bank would fail.
 
 Left out, and why:
-  * tests that load model / material / audio files through assimp, cereal or libsndfile (voxel_tests,
-    mesh_tests, mesh_setup_tests, stochastic_tests, waveguide_tests, rectangular_kernel, filter,
-    reconstruction, multiband_filter, boundary_tests ...): none of the three libraries is here;
+  * tests that load material / audio files through cereal or libsndfile (waveguide_tests,
+    rectangular_kernel, filter, reconstruction, multiband_filter, boundary_tests ...): neither library is
+    here. The tests that only load MODELS (voxel_tests, mesh_tests, mesh_setup_tests, stochastic_tests) do
+    run: assimp's loader is stood in for by the library's own OBJ reader (group "models");
   * gpu_geometry_tests: it builds an OpenCL program from kernel source written inside the test file;
   * equal_energy.cpp: g++ 13 stops with an internal compiler error on it;
   * waveguide_init / verify_compensation_signal: need the generated mesh_impulse_response.h;
@@ -27,7 +28,7 @@ image_source.fast_pressure draws source and receiver anywhere in the room and ne
 find every exact image source within 10 m, matched inside a window of neighbours by distance: it throws
 "No approximate matches." about one time in ten.
 
-Usage: python oracle/ref_recipe/build_tests.py [--all]  -> oracle/_ref/reftest_{core,raytracer,waveguide,frequency_domain}
+Usage: python oracle/ref_recipe/build_tests.py [--all]  -> oracle/_ref/reftest_{core,raytracer,waveguide,frequency_domain,models}
        (--all: also the six-minute nan_in_waveguide run)
 """
 from __future__ import annotations
@@ -55,7 +56,17 @@ GROUPS = {
     "waveguide": [("waveguide", "tests", f + ".cpp") for f in ("main", "build_program")],
     "frequency_domain": [("frequency_domain", "tests", f + ".cpp") for f in ("main", "multiband", "convolution")] +
                         [("frequency_domain", "src", "convolver.cpp")],
+    # the tests that run on the reference's own Wavefront models (demo/assets/test_models): assimp's loader is
+    # stood in for by the library's OBJ reader (reftest_support.cpp)
+    "models": [("core", "tests", "main.cpp"), ("core", "tests", "voxel_tests.cpp"),
+               ("waveguide", "tests", "mesh_tests.cpp"), ("waveguide", "tests", "mesh_setup_tests.cpp"),
+               ("raytracer", "tests", "stochastic_tests.cpp"), ("utilities", "src", "progress_bar.cpp")],
 }
+MODELS = os.path.join(recipe.REF, "demo", "assets", "test_models")
+DEFINES = ['-DSCRATCH_PATH="/tmp"', '-DOBJ_PATH="%s"' % os.path.join(MODELS, "vault.obj"),
+           '-DOBJ_PATH_TUNNEL="%s"' % os.path.join(MODELS, "echo_tunnel.obj"),
+           '-DOBJ_PATH_BEDROOM="%s"' % os.path.join(MODELS, "bedroom.obj"),
+           '-DOBJ_PATH_BAD_BOX="%s"' % os.path.join(MODELS, "small_square.obj")]
 # built and run only on request (`--all`): nan_in_waveguide steps a 56-million-node mesh 432 times through the
 # host-compiled kernel -- six minutes on eight cores (profiles/r02_reference_own_tests.txt has the run)
 SLOW_GROUPS = {
@@ -92,7 +103,7 @@ def build(force: bool = False, slow: bool = False) -> dict[str, str] | None:
         # -include gtest/gtest.h: the standard headers that googletest, GLM and cl.hpp bring in before the
         # reference's own headers are read (several of those use <limits>, <tuple>, size_t without naming them)
         cmd = [recipe.CXX, "-std=gnu++14", "-O1", "-w", "-ffp-contract=off", "-include", "gtest/gtest.h"] + includes + \
-              ['-DSCRATCH_PATH="/tmp"'] + sources + \
+              DEFINES + sources + \
               ["-o", target, "-L" + recipe.OUT, "-l:lib_ref.so", "-Wl,-rpath," + recipe.OUT, "-Wl,-rpath,$ORIGIN",
                "-L" + wvb, "-lwvb200", "-Wl,-rpath," + wvb, "-Wl,-rpath,$ORIGIN/../../wayverb_b200", "-fopenmp", "-pthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -6,7 +6,10 @@ that build. Whether the stand-ins themselves behave is answered by the reference
 the code on and around the path (src/core/tests, src/raytracer/tests, src/waveguide/tests,
 src/frequency_domain/tests -- geometry, tri/cube intersection, indexing, recursive_vector, the reflector
 against its CPU twin, image sources against the exact shoebox solution, multitree, histograms, BRDF,
-"does the program build", the filter bank on noise, convolution) are built by
+"does the program build", the filter bank on noise, convolution, and the tests that run on the reference's
+own models -- voxel walk / flatten / surrounded / compare on the vault, the mesh fixtures on the tunnel
+and the bedroom, bad reflections in the vault; assimp's loader stood in for by the library's OBJ reader)
+are built by
 oracle/ref_recipe/build_tests.py and must pass (its six-minute nan_in_waveguide case -- a 56-million-node
 fitted-wall room stepped 432 times -- runs on request only; profiles/r02_reference_own_tests.txt). What is left out, and the two cases the
 reference contradicts itself on, are listed in that file's docstring."""
@@ -23,7 +26,7 @@ _spec.loader.exec_module(bt)
 BUILT = bt.build()
 pytestmark = pytest.mark.skipif(BUILT is None, reason="no /root/reference and no prebuilt oracle/_ref/reftest_*")
 
-EXPECTED_CASES = {"core": 34, "raytracer": 14, "waveguide": 1, "frequency_domain": 2}
+EXPECTED_CASES = {"core": 34, "raytracer": 14, "waveguide": 1, "frequency_domain": 2, "models": 9}
 
 
 @pytest.mark.parametrize("group", sorted(EXPECTED_CASES))
