@@ -6,7 +6,8 @@ that build. Whether the stand-ins themselves behave is answered by the reference
 the code on and around the path (src/core/tests, src/raytracer/tests, src/waveguide/tests,
 src/frequency_domain/tests -- geometry, tri/cube intersection, indexing, recursive_vector, the reflector
 against its CPU twin, image sources against the exact shoebox solution, multitree, histograms, BRDF,
-"does the program build", the filter bank on noise, convolution, and the tests that run on the reference's
+"does the program build", the biquad cascade against the canonical filter through the reference's filter
+kernels, the filter bank on noise, convolution, and the tests that run on the reference's
 own models -- voxel walk / flatten / surrounded / compare on the vault, the mesh fixtures on the tunnel
 and the bedroom, bad reflections in the vault; assimp's loader stood in for by the library's OBJ reader)
 are built by
@@ -26,7 +27,7 @@ _spec.loader.exec_module(bt)
 BUILT = bt.build()
 pytestmark = pytest.mark.skipif(BUILT is None, reason="no /root/reference and no prebuilt oracle/_ref/reftest_*")
 
-EXPECTED_CASES = {"core": 34, "raytracer": 14, "waveguide": 1, "frequency_domain": 2, "models": 9}
+EXPECTED_CASES = {"core": 34, "raytracer": 14, "waveguide": 6, "frequency_domain": 2, "models": 9}
 
 
 @pytest.mark.parametrize("group", sorted(EXPECTED_CASES))
